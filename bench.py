@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's headline metric on B200, measured through the C ABI.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input: a fresh Graph1 tape, the
+3-layer 4096-wide tanh MLP forward over batch 8192 (f32, column-major), square loss, the reverse sweep
+(evaluate_gradients_once), and with N > 1 the NCCL all-reduce of the weight gradients — BASELINE
+config C4, batch rows sharded over ranks (total work fixed: strong scaling). Rank 0 prints ONE JSON line.
+
+  value      whole-job steps/s with inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e        the same metric through the public API with HOST buffers: every step copies that step's
+             X / target rows from pinned host memory and reads the loss back
+  roofline   the dominant kernel (matmul): tensor-pipe FLOP per launch / measured launch duration vs the
+             measured TF32-dense peak (half the bf16 figure of MEASURED_PEAKS.json)
+  secondary  the other two BASELINE metrics at N=1: reverse-sweep GB/s (C3) and batched-tape grads/s (C2)
+  cpu_baseline  the oracle (a C++ port of the reference's CPU tape; the reference itself is Rust +
+             arrayfire and cannot be built here) timed on the box's host cores on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_TOTAL, D, L = 8192, 4096, 3
+GEMMS_PER_STEP = 8  # 3 forward + 5 backward (X is a constant: no dX)
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores (the ONLY use of oracle/ here)
+# ---------------------------------------------------------------------------------------------------
+def cpu_mlp_steps_per_s(rows: int, threads: int, repeats: int = 1):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((rows, D)).astype(np.float32)
+    Ws = [(rng.standard_normal((D, D)) / np.sqrt(D)).astype(np.float32) for _ in range(L)]
+    bs = [np.full((1, D), 0.01, np.float32) for _ in range(L)]
+    T = rng.standard_normal((rows, D)).astype(np.float32)
+    best = None
+    for _ in range(repeats):
+        _, _, _, secs = oracle_py.mlp_step(X, Ws, bs, T, nthreads=threads)
+        best = secs if best is None else min(best, secs)
+    # a full step is B_TOTAL/rows of these (every GEMM, elementwise pass and reduction is linear in rows)
+    return 1.0 / (best * (B_TOTAL / rows)), best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_cores()
+    rows = 128
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_mlp_steps_per_s(rows, threads)
+    vals, times = [], []
+    for _ in range(max(1, min(args.steps, 5))):
+        v, t = cpu_mlp_steps_per_s(rows, threads)
+        vals.append(v)
+        times.append(t)
+    v = float(np.mean(vals))
+    sample = f"{rows} of {B_TOTAL} batch rows at full width D={D}, L={L}; steps/s scaled by {B_TOTAL // rows}x (work is linear in rows)"
+    line = {"impl": "reference", "metric": "MLP fwd+bwd steps/s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C4 3-layer tanh MLP {D}-wide, batch {B_TOTAL}, f32, Graph1 fwd + reverse sweep", "global_batch": B_TOTAL},
+            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference (Rust crate gad + arrayfire) cannot be built in this image; this is oracle/, a C++ port of its CPU tape"}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import gad_b200 as gb
+    from gad_b200 import workloads as wl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = gb.Context(local_rank)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+    comm = None
+    if world > 1:
+        obj = [gb.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        comm = gb.Comm(ctx, world, rank, obj[0])
+
+    rows = B_TOTAL // world
+    # synthetic data of the named shapes: X~N(0,1) seed 5, W_l~N(0,1/D) seeds 6-8, b=0.01, target~N(0,1) seed 9
+    X = ctx.random((rows, D), 5 + 100 * rank, normal=True, a=0.0, b=1.0)
+    T = ctx.random((rows, D), 9 + 100 * rank, normal=True, a=0.0, b=1.0)
+    Ws = [ctx.random((D, D), 6 + l, normal=True, a=0.0, b=1.0 / np.sqrt(D)) for l in range(L)]
+    bs = [ctx.array(np.full((1, D), 0.01, np.float32)) for _ in range(L)]
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(steps):
+            fn()
+        e1.record(ext)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    keep = {}
+
+    def step_resident():
+        keep["out"] = wl.mlp_step(ctx, X, Ws, bs, T, comm)
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches()
+    ctx.profile_begin()
+    ms = timed(step_resident, args.steps)
+    prof = ctx.profile_end()
+    launches = ctx.launches() - launches0
+    clocks = sampler.summary() if rank == 0 else None
+    loss_val = keep["out"][0].item()
+    steps_per_s = args.steps / (ms / 1000.0)
+
+    # ---- e2e: host buffers in, loss out, every step
+    hX = torch.empty((rows * D,), dtype=torch.float32).pin_memory()
+    hT = torch.empty((rows * D,), dtype=torch.float32).pin_memory()
+    hX.normal_(generator=torch.Generator().manual_seed(5 + rank))
+    hT.normal_(generator=torch.Generator().manual_seed(9 + rank))
+    nX, nT = hX.numpy(), hT.numpy()
+    dX, dT = ctx.empty((rows, D)), ctx.empty((rows, D))
+    e2e_loss = {}
+
+    def step_e2e():
+        dX.upload(nX)
+        dT.upload(nT)
+        out = wl.mlp_step(ctx, dX, Ws, bs, dT, comm)
+        e2e_loss["v"] = out[0].item()  # device -> host read of the step's result
+
+    for _ in range(3):
+        step_e2e()
+    e2e_steps = max(1, args.steps)
+    ms_e2e = timed(step_e2e, e2e_steps)
+    e2e = {"value": e2e_steps / (ms_e2e / 1000.0), "unit": "steps/s", "h2d_bytes_per_step": int(2 * rows * D * 4 * world),
+           "d2h_bytes_per_step": int(4 * world), "ms_per_step": ms_e2e / e2e_steps}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    tf32_peak = pk["bf16_tflops_sustained"] / 2.0  # TF32 dense = half of bf16; kernel timed inside a long step
+    gemm = prof["matmul"]
+    gemm_ms = gemm["ms"] / max(1, gemm["launches"])
+    logical_flop = 2.0 * rows * D * D
+    tc_path = os.environ.get("GADCU_GEMM_PATH", "auto")
+    mma_flop = 3.0 * logical_flop  # 3xTF32: three tensor-core products per logical product
+    achieved = mma_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+                "traffic": None, "kernel": "matmul (fwd / dA / dW), 3xTF32",
+                "logical_fp32_tflops": logical_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
+                "peak_source": f"{pk['source']}: bf16_tflops_sustained/2", "avg_launch_ms": gemm_ms, "launches": gemm["launches"],
+                "share_of_step": gemm["ms"] / ms if ms > 0 else None, "gemm_path": tc_path}
+
+    line = {"metric": "MLP fwd+bwd steps/s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C4 3-layer tanh MLP {D}-wide, batch {B_TOTAL}, f32, Graph1 fwd + reverse sweep", "global_batch": B_TOTAL,
+                       "rows_per_gpu": rows, "parallelism": f"dp{world} (batch rows sharded, NCCL allreduce of weight grads)",
+                       "l2": "inputs larger than L2 (activations 128 MiB, weights 64 MiB each vs 126 MB L2)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "kernel_time_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}, "loss": loss_val}
+
+    if world == 1 and not args.headline_only:
+        try:
+            line["secondary"] = secondary_metrics(ctx, ext, torch, gb, wl, pk, args)
+        except Exception as e:  # the headline line must survive
+            line["secondary"] = {"error": repr(e)}
+        try:
+            threads = host_cores()
+            rows_s = 128
+            v, t = cpu_mlp_steps_per_s(rows_s, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "seconds": t,
+                                    "sample": f"{rows_s} of {B_TOTAL} batch rows at full width D={D}, L={L}; scaled by {B_TOTAL // rows_s}x"}
+        except Exception as e:
+            line["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def secondary_metrics(ctx, ext, torch, gb, wl, pk, args):
+    out = {}
+
+    def ev_time(fn, reps):
+        ctx.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(reps):
+            fn()
+        e1.record(ext)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # ---- C3: reverse sweep of the 64 Mi-element elementwise tape
+    n = 64 * 1024 * 1024
+    x = ctx.random((n,), 3, a=-1.0, b=1.0)
+    y = ctx.random((n,), 4, a=0.5, b=2.0)
+    g = gb.Graph1(ctx)
+    vx, vy, z = wl.c3_forward(g, x, y)
+    keep = {}
+
+    def sweep():
+        keep["s"] = g.evaluate_gradients(z.gid(), 1.0)
+
+    for _ in range(3):
+        sweep()
+    l0 = ctx.launches()
+    ms_sweep = ev_time(sweep, 10)
+    sweep_launches = (ctx.launches() - l0) // 10
+    alg_bytes = 4 * n * 4  # read x, y; write dz/dx, dz/dy
+    gbs = alg_bytes / (ms_sweep * 1e-3) / 1e9
+
+    def fwd_bwd():
+        keep["r"] = wl.c3_step(ctx, x, y)
+
+    for _ in range(3):
+        fwd_bwd()
+    ms_fb = ev_time(fwd_bwd, 10)
+    out["grad_sweep"] = {
+        "metric": "grad-sweep HBM GB/s", "workload": "C3 64Mi-element exp/log/mul/add + sum, f32, reverse sweep", "value": gbs, "unit": "GB/s",
+        "ms_per_sweep": ms_sweep, "launches_per_sweep": int(sweep_launches),
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                     "frac_of_8TBs": gbs / 8000.0, "traffic": None, "algorithmic_bytes": alg_bytes,
+                     "note": "algorithmic = 4 passes (read x,y; write gx,gy); the per-node sweep materialises more (see DESIGN.md)"},
+        "fwd_plus_sweep_ms": ms_fb, "fwd_plus_sweep_gbs": 6 * n * 4 / (ms_fb * 1e-3) / 1e9}
+    del keep, g, vx, vy, z, x, y
+
+    # ---- C2: batched scalar tapes, 2^20 lanes x Rosenbrock-64, f64
+    lanes, N = 1 << 20, 64
+    cols = [ctx.random((lanes,), 200 + i, dtype=gb.F64, a=-1.2, b=1.2) for i in range(N)]
+    res = {}
+
+    def batched():
+        res["r"] = wl.rosenbrock_batched_gradients(ctx, cols)
+
+    batched()
+    ctx.profile_begin()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        batched()
+    ctx.synchronize()
+    wall = (time.perf_counter() - t0) / reps
+    prof = ctx.profile_end()
+    k_ms = prof["tile_transpose"]["ms"] / max(1, prof["tile_transpose"]["launches"])
+    stats = res["r"][3].program_stats()
+    gps = lanes / (k_ms * 1e-3) if k_ms > 0 else 0.0
+    alg = 2 * N * 8  # bytes per gradient: read 64 f64, write 64 f64
+    out["batched_tape"] = {
+        "metric": "batched-tape grads/s", "workload": f"C2 {lanes} lanes x Rosenbrock-{N}, f64, one tape per lane", "value": gps,
+        "unit": "grads/s", "kernel_ms": k_ms, "end_to_end_ms_incl_tape_build": wall * 1e3, "end_to_end_grads_per_s": lanes / wall,
+        "program_instructions": stats["instructions"], "program_slots": stats["slots"],
+        "roofline": {"bound": "hbm", "achieved": gps * alg / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": gps * alg / 1e9 / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_gradient": alg}}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--headline-only", action="store_true", help="skip the secondary metrics and the CPU baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

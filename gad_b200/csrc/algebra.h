@@ -1,0 +1,335 @@
+// algebra.h — gad's algebras over device arrays: Check (dims), Eval (kernels), Graph1/GraphN (tape).
+// One abstract interface carries every operator of the AfAlgebra bundle
+// (gad/src/arrayfire.rs:9-37); VJP bodies are written once against it, so the same code runs the
+// Graph1 sweep (gradient algebra = Eval, gad/src/graph.rs:250-256) and records the GraphN sweep
+// (gradient algebra = the graph itself, graph.rs:294-300).
+#pragma once
+#include <functional>
+#include <map>
+#include <queue>
+
+#include "core.h"
+#include "kernels.h"
+
+namespace gadcu {
+
+const std::string& last_error();
+
+template <class F>
+gadcu_status guard(F f) {
+  try {
+    f();
+    return GADCU_OK;
+  } catch (const GadError& e) {
+    set_last_error(e.msg);
+    return e.status;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return GADCU_ERR_INVALID;
+  }
+}
+
+// store.rs:12-16 — ordered by (arena, index); index 0 encodes `None`.
+struct Id {
+  uint32_t arena = 0, index = 0;
+  bool some() const { return index != 0; }
+  bool operator<(const Id& o) const { return arena != o.arena ? arena < o.arena : index < o.index; }
+  bool operator==(const Id& o) const { return arena == o.arena && index == o.index; }
+  Id next_id() const { return Id{arena, index + 1}; }
+};
+
+// graph.rs:35-43
+struct Value {
+  ArrayRef data;
+  Id id;
+  Value() = default;
+  Value(ArrayRef d, Id i = Id{}) : data(std::move(d)), id(i) {}
+};
+
+// ---- Check: dimension rules. Throw GadError with gad's error variant. -----------
+namespace check {
+Dim4 equal(const char* name, std::initializer_list<const Dim4*> dims);
+Dim4 equal(const char* name, const std::vector<const Dim4*>& dims);
+Dim4 select_argmax(const Dim4& v0, const Dim4& v1, const Dim4* r0, const Dim4* r1);
+Dim4 flat(const Dim4& v);
+Dim4 moddims(const Dim4& v, const Dim4& d);
+Dim4 tile_as(const Dim4& v, const Dim4& r);
+Dim4 sum_as(const Dim4& v, const Dim4& r);
+void as_scalar(const Dim4& v);
+void dot(const Dim4& a, const Dim4& b);
+Dim4 reduced(const char* name, const Dim4& v, const Dim4& r);
+Dim4 transpose(const Dim4& v);
+Dim4 matmul(const Dim4& a, const Dim4& b, MatProp p1, MatProp p2);
+}  // namespace check
+
+}  // namespace gadcu
+
+struct gadcu_store;
+
+// The algebra interface (the C handle type is this class).
+struct gadcu_algebra {
+  gadcu_ctx* ctx = nullptr;
+  explicit gadcu_algebra(gadcu_ctx* c) : ctx(c) {}
+  virtual ~gadcu_algebra() = default;
+  using Value = gadcu::Value;
+  using Dim4 = gadcu::Dim4;
+  using MatProp = gadcu::MatProp;
+
+  virtual gadcu_algebra_kind kind() const = 0;
+  virtual gadcu_algebra* clone() const = 0;
+  virtual size_t num_nodes() const { return 0; }
+  virtual bool is_eval() const { return false; }
+  // LinkedAlgebra::link (linked.rs): data view for eval algebras, identity for graphs.
+  virtual Value link(const Value& v) { return v; }
+
+  // CoreAlgebra
+  virtual Value variable(gadcu::ArrayRef data) = 0;
+  virtual Value constant(gadcu::ArrayRef data) = 0;
+  virtual Value add(const Value& a, const Value& b) = 0;
+  virtual Value add_all(const std::vector<const Value*>& vs);  // core.rs:27-37 left fold
+  // ArithAlgebra
+  virtual Value sub(const Value& a, const Value& b) = 0;
+  virtual Value mul(const Value& a, const Value& b) = 0;
+  virtual Value zeros(const Value& v) = 0;
+  virtual Value ones(const Value& v) = 0;
+  virtual Value neg(const Value& v) = 0;
+  // ConstArithAlgebra
+  virtual Value setc(const Value& v, double c, bool is_int) = 0;
+  virtual Value addc(const Value& v, double c, bool is_int) = 0;
+  virtual Value mulc(const Value& v, double c, bool is_int) = 0;
+  virtual Value powc(const Value& v, double c, bool is_int) = 0;
+  // AnalyticAlgebra
+  virtual Value exp(const Value& v) = 0;
+  virtual Value log(const Value& v) = 0;
+  virtual Value log1p(const Value& v) = 0;
+  virtual Value sin(const Value& v) = 0;
+  virtual Value cos(const Value& v) = 0;
+  virtual Value tanh(const Value& v) = 0;
+  virtual Value sigmoid(const Value& v) = 0;
+  virtual Value reciprocal(const Value& v) = 0;
+  virtual Value sqrt(const Value& v) = 0;
+  virtual Value div(const Value& a, const Value& b) = 0;
+  virtual Value pow(const Value& v, const Value& p);  // analytic.rs:48-55 default: exp(p * log v)
+  // CompareAlgebra (defaults: compare.rs:17-55)
+  virtual Value select_argmax(const Value& v0, const Value& v1, const Value* r0, const Value* r1) = 0;
+  virtual Value min(const Value& a, const Value& b) { return select_argmax(a, b, &b, &a); }
+  virtual Value max(const Value& a, const Value& b) { return select_argmax(a, b, &a, &b); }
+  virtual Value abs(const Value& v);
+  virtual Value sign(const Value& v);
+  virtual Value relu(const Value& v);
+  // ArrayAlgebra
+  virtual Value flat(const Value& v) = 0;
+  virtual Value moddims(const Value& v, const Dim4& d) = 0;
+  virtual Value tile_as(const Value& v, const Dim4& d) = 0;
+  virtual Value sum_as(const Value& v, const Dim4& d) = 0;
+  virtual Value constant_as(const Value& scalar, const Dim4& d) = 0;
+  virtual Value as_scalar(const Value& v) = 0;
+  virtual Value scale(const Value& lambda, const Value& v) = 0;
+  virtual Value dot(const Value& a, const Value& b) = 0;
+  virtual Value norm2(const Value& v) { return dot(v, v); }  // array.rs:42-44
+  // MatrixAlgebra
+  virtual Value matmul(const Value& a, const Value& b, MatProp p1, MatProp p2) = 0;
+  virtual Value matmul_nn(const Value& a, const Value& b) { return matmul(a, b, MatProp{}, MatProp{}); }
+  virtual Value transpose(const Value& v, bool conjugate) = 0;
+  // ArrayCompareAlgebra
+  virtual Value max_as(const Value& v, const Dim4& d) = 0;
+  virtual Value argmax_as(const Value& v, const Dim4& d) = 0;
+  virtual Value softmax_as(const Value& v, const Dim4& d) = 0;
+
+  // GradientStore::add_gradient's `current + new` when `current` may be consumed (store.rs:52).
+  virtual Value accumulate(Value&& current, const Value& value) { return add(current, value); }
+};
+
+namespace gadcu {
+
+using Algebra = ::gadcu_algebra;
+
+// ---- Eval over device arrays: dims check on the host, then one kernel ---------------------------
+class EvalAlgebra final : public Algebra {
+ public:
+  explicit EvalAlgebra(gadcu_ctx* c) : Algebra(c) {}
+  gadcu_algebra_kind kind() const override { return GADCU_EVAL; }
+  gadcu_algebra* clone() const override { return new EvalAlgebra(ctx); }
+  bool is_eval() const override { return true; }
+  Value link(const Value& v) override { return Value(v.data); }
+
+  Value variable(ArrayRef data) override { return Value(std::move(data)); }
+  Value constant(ArrayRef data) override { return Value(std::move(data)); }
+  Value add(const Value& a, const Value& b) override;
+  Value sub(const Value& a, const Value& b) override;
+  Value mul(const Value& a, const Value& b) override;
+  Value zeros(const Value& v) override;
+  Value ones(const Value& v) override;
+  Value neg(const Value& v) override;
+  Value setc(const Value& v, double c, bool is_int) override;
+  Value addc(const Value& v, double c, bool is_int) override;
+  Value mulc(const Value& v, double c, bool is_int) override;
+  Value powc(const Value& v, double c, bool is_int) override;
+  Value exp(const Value& v) override;
+  Value log(const Value& v) override;
+  Value log1p(const Value& v) override;
+  Value sin(const Value& v) override;
+  Value cos(const Value& v) override;
+  Value tanh(const Value& v) override;
+  Value sigmoid(const Value& v) override;
+  Value reciprocal(const Value& v) override;
+  Value sqrt(const Value& v) override;
+  Value div(const Value& a, const Value& b) override;
+  Value pow(const Value& v, const Value& p) override;  // af::pow (analytic.rs:124-127)
+  Value select_argmax(const Value& v0, const Value& v1, const Value* r0, const Value* r1) override;
+  Value min(const Value& a, const Value& b) override;  // af::minof (compare.rs:82-86)
+  Value max(const Value& a, const Value& b) override;  // af::maxof (compare.rs:88-92)
+  Value flat(const Value& v) override;
+  Value moddims(const Value& v, const Dim4& d) override;
+  Value tile_as(const Value& v, const Dim4& d) override;
+  Value sum_as(const Value& v, const Dim4& d) override;
+  Value constant_as(const Value& scalar, const Dim4& d) override;
+  Value as_scalar(const Value& v) override;
+  Value scale(const Value& lambda, const Value& v) override;
+  Value dot(const Value& a, const Value& b) override;
+  Value matmul(const Value& a, const Value& b, MatProp p1, MatProp p2) override;
+  Value transpose(const Value& v, bool conjugate) override;
+  Value max_as(const Value& v, const Dim4& d) override;
+  Value argmax_as(const Value& v, const Dim4& d) override;
+  Value softmax_as(const Value& v, const Dim4& d) override;
+  Value accumulate(Value&& current, const Value& value) override;
+
+  // One kernel: out = [acc +] op(ins...). In place when `acc` is uniquely owned.
+  ArrayRef fused(k::EwOp op, ArrayRef acc, std::initializer_list<const ArrayRef*> ins, double c = 0.0, double c2 = 0.0);
+  // One GEMM: out = [acc +] op(a)*op(b)
+  ArrayRef matmul_acc(ArrayRef acc, const ArrayRef& a, const ArrayRef& b, MatProp p1, MatProp p2);
+  // sum_as with the accumulation folded into the last reduction pass
+  ArrayRef sum_as_acc(ArrayRef acc, const ArrayRef& v, const Dim4& d);
+
+ private:
+  Value unary(k::EwOp op, const Value& v, double c = 0.0);
+  Value binary(k::EwOp op, const char* name, const Value& a, const Value& b);
+  ArrayRef reduce_as(k::RedOp op, const ArrayRef& v, const Dim4& rd, ArrayRef acc);
+};
+
+// ---- the tape ------------------------------------------------------------------------------------
+enum class Op : uint8_t {
+  VARIABLE, ADD, ADD_ALL, NEG, SUB, MUL, ADDC, MULC, POWC, EXP, LOG, LOG1P, SIN, COS, TANH, SIGMOID, RECIPROCAL, SQRT, DIV,
+  SELECT_ARGMAX, MODDIMS, TILE_AS, SUM_AS, CONSTANT_AS, AS_SCALAR, SCALE, DOT, MATMUL, TRANSPOSE, MAX_AS, SOFTMAX_AS, CUSTOM
+};
+
+struct CustomVjp {
+  gadcu_vjp_fn fn = nullptr;
+  void* user = nullptr;
+  void (*drop)(void*) = nullptr;
+  ~CustomVjp() { if (drop && user) drop(user); }
+};
+
+// graph.rs:46-62: inputs + update function. The update function is an op code plus the captured
+// forward values instead of a boxed closure, so the sweep can choose fused kernels per node.
+struct Node {
+  Op op = Op::VARIABLE;
+  bool has_update = false;
+  std::vector<Id> inputs;    // pushed on the heap after the update (index 0 = None)
+  std::vector<Value> saved;  // captured forward values (clones are O(1) handle copies)
+  double c = 0.0;
+  bool c_is_int = false;
+  Dim4 d;                    // op-specific dims (vdims or rdims)
+  MatProp p1, p2;
+  bool flag = false;
+  // forward dims captured by make_generic_node for the wrapper's check (graph.rs:149,156)
+  Dim4 fwd_dims;
+  bool fwd_scalar = false;
+  gadcu_dtype fwd_dtype = GADCU_F32;
+  std::shared_ptr<CustomVjp> custom;
+  void clear() { inputs.clear(); saved.clear(); custom.reset(); has_update = false; }
+};
+
+}  // namespace gadcu
+
+// store.rs:60-140 — one map serves Graph1 (values carry no id) and GraphN (values carry ids).
+struct gadcu_store {
+  std::map<gadcu::Id, gadcu::Value> values;
+  const gadcu::Value* get(gadcu::Id id) const {
+    auto it = values.find(id);
+    return it == values.end() ? nullptr : &it->second;
+  }
+  void insert(gadcu::Id id, gadcu::Value v) { values[id] = std::move(v); }
+  // store.rs:44-55
+  void add_gradient(gadcu::Algebra& graph, gadcu::Id id, const gadcu::Value& value);
+  // fused: contribution = op(ins...) computed and accumulated by one kernel (Graph1 + fusion only)
+  void add_fused(gadcu::EvalAlgebra& ev, gadcu::Id id, gadcu::k::EwOp op, std::initializer_list<const gadcu::ArrayRef*> ins,
+                 double c = 0.0, double c2 = 0.0);
+  // batched-tape stats
+  uint64_t program_instructions = 0, program_slots = 0;
+};
+
+namespace gadcu {
+
+using Store = ::gadcu_store;
+
+class GraphAlgebra final : public Algebra {
+ public:
+  // `eval` computes forward values (graph.rs:19-22 `eval: C::EvalAlgebra`): EvalAlgebra for device
+  // arrays, or the symbolic per-lane algebra of batched.cu — Graph<Config<E>> for any E.
+  GraphAlgebra(gadcu_ctx* c, bool higher_order, std::shared_ptr<Algebra> eval = nullptr);
+  gadcu_algebra_kind kind() const override { return kind_override_ ? kind_override_ : (higher_order_ ? GADCU_GRAPHN : GADCU_GRAPH1); }
+  gadcu_algebra* clone() const override { return new GraphAlgebra(*this); }  // keeps arena id
+  size_t num_nodes() const override { return nodes_.size(); }
+  Algebra& eval() { return *eval_; }
+  void set_kind(gadcu_algebra_kind k) { kind_override_ = k; }
+  bool is_variable(Id id) const { return id.arena == arena_id_ && id.index >= 1 && id.index <= nodes_.size() && nodes_[id.index - 1].op == Op::VARIABLE && !nodes_[id.index - 1].has_update; }
+
+  Value variable(ArrayRef data) override;
+  Value constant(ArrayRef data) override { return Value(std::move(data)); }
+  Value add(const Value& a, const Value& b) override;
+  Value add_all(const std::vector<const Value*>& vs) override;
+  Value sub(const Value& a, const Value& b) override;
+  Value mul(const Value& a, const Value& b) override;
+  Value zeros(const Value& v) override { return Value(eval_->zeros(v).data); }
+  Value ones(const Value& v) override { return Value(eval_->ones(v).data); }
+  Value neg(const Value& v) override;
+  Value setc(const Value& v, double c, bool is_int) override { return Value(eval_->addc(v, c, is_int).data); }  // sic, const_arith.rs:134-137
+  Value addc(const Value& v, double c, bool is_int) override;
+  Value mulc(const Value& v, double c, bool is_int) override;
+  Value powc(const Value& v, double c, bool is_int) override;
+  Value exp(const Value& v) override;
+  Value log(const Value& v) override;
+  Value log1p(const Value& v) override;
+  Value sin(const Value& v) override;
+  Value cos(const Value& v) override;
+  Value tanh(const Value& v) override;
+  Value sigmoid(const Value& v) override;
+  Value reciprocal(const Value& v) override;
+  Value sqrt(const Value& v) override;
+  Value div(const Value& a, const Value& b) override;
+  Value select_argmax(const Value& v0, const Value& v1, const Value* r0, const Value* r1) override;
+  Value flat(const Value& v) override;
+  Value moddims(const Value& v, const Dim4& d) override;
+  Value tile_as(const Value& v, const Dim4& d) override;
+  Value sum_as(const Value& v, const Dim4& d) override;
+  Value constant_as(const Value& scalar, const Dim4& d) override;
+  Value as_scalar(const Value& v) override;
+  Value scale(const Value& lambda, const Value& v) override;
+  Value dot(const Value& a, const Value& b) override;
+  Value matmul(const Value& a, const Value& b, MatProp p1, MatProp p2) override;
+  Value transpose(const Value& v, bool conjugate) override;
+  Value max_as(const Value& v, const Dim4& d) override;
+  Value argmax_as(const Value& v, const Dim4& d) override { return Value(eval_->argmax_as(v, d).data); }
+  Value softmax_as(const Value& v, const Dim4& d) override;
+
+  // graph.rs:106-165
+  Value make_node(ArrayRef data, Node node);
+  Value make_custom(ArrayRef data, std::vector<Id> inputs, std::shared_ptr<CustomVjp> vjp);
+
+  // graph.rs:263-290 / 307-318
+  std::unique_ptr<Store> evaluate_gradients(Id id, ArrayRef seed, bool once);
+  std::unique_ptr<Store> compute_gradients(Id id, const Value& seed);
+
+ private:
+  std::unique_ptr<Store> sweep(Algebra& ga, Id gid, Value gradient, bool once);
+  void vjp(const Node& n, Algebra& ga, Store& store, const Value& g);
+
+  bool higher_order_;
+  gadcu_algebra_kind kind_override_ = gadcu_algebra_kind(0);
+  uint32_t arena_id_;
+  std::shared_ptr<Algebra> eval_;
+  std::vector<Node> nodes_;
+};
+
+}  // namespace gadcu

@@ -1,0 +1,14 @@
+// batched.h — batched scalar tapes: thousands of independent gad scalar tapes, one per lane, in
+// structure-of-arrays layout (north-star subsystem 4).
+#pragma once
+#include "algebra.h"
+
+namespace gadcu {
+
+// A GraphAlgebra whose eval algebra is the symbolic per-lane algebra (kind GADCU_BATCHED1).
+std::unique_ptr<GraphAlgebra> make_batched(gadcu_ctx* ctx, gadcu_dtype dt, uint64_t lanes);
+// Graph1::evaluate_gradients over lanes: symbolic sweep, then one kernel computes the gradients of
+// all variables. Other store entries stay symbolic and are computed when read.
+std::unique_ptr<Store> batched_evaluate_gradients(GraphAlgebra& g, Id id, ArrayRef seed, bool once);
+
+}  // namespace gadcu

@@ -1,0 +1,340 @@
+// runtime.cu — context, caching allocator, arrays, CUDA-graph capture.
+#include <cstring>
+
+#include "algebra.h"
+#include "kernels.h"
+
+namespace gadcu {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const std::string& last_error() { return g_last_error; }
+void fail(int status, const std::string& msg) { throw GadError(status, msg); }
+
+std::string Dim4::str() const {
+  return "[" + std::to_string(d[0]) + " " + std::to_string(d[1]) + " " + std::to_string(d[2]) + " " + std::to_string(d[3]) + "]";
+}
+
+// ---- pool ---------------------------------------------------------------------------------------
+Pool::~Pool() {
+  for (auto& kv : free_blocks) cudaFree(kv.second);
+}
+void* Pool::take(size_t bytes) {
+  bytes = round_up(bytes);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = free_blocks.find(bytes);
+    if (it != free_blocks.end()) {
+      void* p = it->second;
+      free_blocks.erase(it);
+      in_use += bytes;
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t err = cudaMalloc(&p, bytes);
+  if (err != cudaSuccess) {
+    // release cached blocks and retry once
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (auto& kv : free_blocks) { cudaFree(kv.second); reserved -= kv.first; }
+      free_blocks.clear();
+    }
+    cudaGetLastError();
+    err = cudaMalloc(&p, bytes);
+    if (err != cudaSuccess) fail(GADCU_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(err));
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  reserved += bytes;
+  in_use += bytes;
+  return p;
+}
+void Pool::put(void* p, size_t bytes) {
+  bytes = round_up(bytes);
+  std::lock_guard<std::mutex> lk(mu);
+  free_blocks.emplace(bytes, p);
+  in_use -= bytes;
+}
+
+void Buffer::release() {
+  if (refs.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+    if (pool && ptr) pool->put(ptr, bytes);
+    delete this;
+  }
+}
+
+ArrayRef new_array(gadcu_ctx* ctx, gadcu_dtype dt, const Dim4& dims, bool is_scalar) {
+  auto* buf = new Buffer;
+  Ref<Buffer> bref(buf, false);
+  buf->ctx = ctx;
+  buf->bytes = dims.elements() * dtype_size(dt);
+  buf->pool = ctx->active_pool();
+  buf->ptr = buf->pool->take(buf->bytes);
+  auto* a = new gadcu_array;
+  a->buf = bref;
+  a->dims = dims;
+  a->phys = dims;
+  a->dtype = dt;
+  a->is_scalar = is_scalar;
+  a->ctx = ctx;
+  return ArrayRef(a, false);
+}
+
+ArrayRef view_array(const ArrayRef& src, const Dim4& dims, const Dim4& phys, bool is_scalar) {
+  auto* a = new gadcu_array;
+  a->buf = src->buf;
+  a->dims = dims;
+  a->phys = phys;
+  a->dtype = src->dtype;
+  a->is_scalar = is_scalar;
+  a->ctx = src->ctx;
+  return ArrayRef(a, false);
+}
+
+ArrayRef materialize(const ArrayRef& a) {
+  if (a->symbolic()) return force_symbolic(a);
+  if (!a->lazy()) return a;
+  ArrayRef out = new_array(a->ctx, a->dtype, a->dims, a->is_scalar);
+  if (a->bcast1()) {
+    k::EwArgs e;
+    e.dt = a->dtype; e.nin = 1; e.in[0] = a->ptr(); e.bcast[0] = true; e.out = out->ptr(); e.n = a->elements();
+    k::launch_ew(a->ctx, k::EwOp::COPY, e);
+  } else {
+    k::launch_tile(a->ctx, a->dtype, a->ptr(), a->phys, out->ptr(), a->dims);
+  }
+  return out;
+}
+
+}  // namespace gadcu
+
+using namespace gadcu;
+
+struct gadcu_capture {
+  gadcu_ctx* ctx = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::shared_ptr<Pool> pool;
+  uint64_t launches = 0;
+};
+
+extern "C" {
+
+const char* gadcu_last_error(void) { return gadcu::last_error().c_str(); }
+const char* gadcu_version(void) { return "gadcu 0.1 (sm_100a)"; }
+
+gadcu_status gadcu_ctx_create(int device, gadcu_ctx** out) {
+  return guard([&] {
+    GADCU_CUDA(cudaSetDevice(device));
+    auto* ctx = new gadcu_ctx;
+    ctx->device = device;
+    GADCU_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    GADCU_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    GADCU_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->pool = std::make_shared<Pool>();
+    GADCU_CUDA(cudaMallocHost(&ctx->pinned_scratch, 4096));
+    *out = ctx;
+  });
+}
+
+gadcu_status gadcu_ctx_destroy(gadcu_ctx* ctx) {
+  return guard([&] {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->side_stream);
+    if (ctx->pinned_scratch) cudaFreeHost(ctx->pinned_scratch);
+    if (ctx->dev_scratch) cudaFree(ctx->dev_scratch);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->side_stream);
+    delete ctx;
+  });
+}
+
+gadcu_status gadcu_ctx_synchronize(gadcu_ctx* ctx) {
+  return guard([&] { GADCU_CUDA(cudaStreamSynchronize(ctx->stream)); });
+}
+void* gadcu_ctx_stream(gadcu_ctx* ctx) { return ctx->stream; }
+gadcu_status gadcu_ctx_set_fusion(gadcu_ctx* ctx, int fuse) {
+  ctx->fuse = fuse != 0;
+  return GADCU_OK;
+}
+gadcu_status gadcu_ctx_memory_stats(gadcu_ctx* ctx, uint64_t* in_use, uint64_t* reserved, uint64_t* launches) {
+  std::lock_guard<std::mutex> lk(ctx->pool->mu);
+  if (in_use) *in_use = ctx->pool->in_use;
+  if (reserved) *reserved = ctx->pool->reserved;
+  if (launches) *launches = ctx->launches.load();
+  return GADCU_OK;
+}
+
+gadcu_status gadcu_ctx_profile_begin(gadcu_ctx* ctx) {
+  return guard([&] {
+    for (auto& v : ctx->prof_events) {
+      for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+      v.clear();
+    }
+    ctx->profiling = true;
+  });
+}
+gadcu_status gadcu_ctx_profile_end(gadcu_ctx* ctx, double* ms4, uint64_t* count4) {
+  return guard([&] {
+    ctx->profiling = false;
+    GADCU_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < 4; c++) {
+      double total = 0.0;
+      for (auto& e : ctx->prof_events[c]) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.first, e.second);
+        total += ms;
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+      }
+      if (ms4) ms4[c] = total;
+      if (count4) count4[c] = ctx->prof_events[c].size();
+      ctx->prof_events[c].clear();
+    }
+  });
+}
+
+gadcu_status gadcu_array_alloc(gadcu_ctx* ctx, gadcu_dtype dt, const gadcu_dim4* dims, gadcu_array** out) {
+  return guard([&] { *out = new_array(ctx, dt, Dim4(*dims)).detach(); });
+}
+gadcu_status gadcu_array_from_host(gadcu_ctx* ctx, gadcu_dtype dt, const gadcu_dim4* dims, const void* host, gadcu_array** out) {
+  return guard([&] {
+    ArrayRef a = new_array(ctx, dt, Dim4(*dims));
+    GADCU_CUDA(cudaMemcpyAsync(a->ptr(), host, a->buf->bytes, cudaMemcpyHostToDevice, ctx->stream));
+    GADCU_CUDA(cudaStreamSynchronize(ctx->stream));  // `host` may be pageable and reused by the caller
+    *out = a.detach();
+  });
+}
+gadcu_status gadcu_array_upload(gadcu_array* a, const void* pinned_host, void* stream_or_null) {
+  return guard([&] {
+    if (a->lazy()) fail(GADCU_ERR_INVALID, "upload into a lazy view");
+    cudaStream_t s = stream_or_null ? static_cast<cudaStream_t>(stream_or_null) : a->ctx->stream;
+    GADCU_CUDA(cudaMemcpyAsync(a->ptr(), pinned_host, a->elements() * a->elem_size(), cudaMemcpyHostToDevice, s));
+  });
+}
+gadcu_status gadcu_array_to_host(const gadcu_array* a, void* host) {
+  return guard([&] {
+    ArrayRef dense = materialize(ArrayRef(const_cast<gadcu_array*>(a), true));
+    GADCU_CUDA(cudaMemcpyAsync(host, dense->ptr(), dense->elements() * dense->elem_size(), cudaMemcpyDeviceToHost, a->ctx->stream));
+    GADCU_CUDA(cudaStreamSynchronize(a->ctx->stream));
+  });
+}
+gadcu_status gadcu_array_retain(gadcu_array* a) { if (a) a->retain(); return GADCU_OK; }
+gadcu_status gadcu_array_release(gadcu_array* a) { if (a) a->release(); return GADCU_OK; }
+gadcu_status gadcu_array_dims(const gadcu_array* a, gadcu_dim4* out) { *out = a->dims.c(); return GADCU_OK; }
+gadcu_dtype gadcu_array_dtype(const gadcu_array* a) { return a->dtype; }
+int gadcu_array_is_scalar(const gadcu_array* a) { return a->is_scalar ? 1 : 0; }
+void* gadcu_array_device_ptr(const gadcu_array* a) {
+  if (a->lazy() || a->symbolic()) return nullptr;
+  return a->ptr();
+}
+gadcu_status gadcu_scalar_from_host(gadcu_ctx* ctx, gadcu_dtype dt, double v, gadcu_array** out) {
+  return guard([&] {
+    ArrayRef a = new_array(ctx, dt, Dim4(), true);
+    k::launch_fill(ctx, dt, a->ptr(), 1, v);
+    *out = a.detach();
+  });
+}
+gadcu_status gadcu_scalar_to_host(const gadcu_array* a, double* out) {
+  return guard([&] {
+    if (a->symbolic() || a->phys.elements() != 1) fail(GADCU_ERR_INVALID, "scalar_to_host on a non-scalar");
+    gadcu_ctx* ctx = a->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    GADCU_CUDA(cudaMemcpyAsync(ctx->pinned_scratch, a->ptr(), a->elem_size(), cudaMemcpyDeviceToHost, ctx->stream));
+    GADCU_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = a->dtype == GADCU_F32 ? double(*static_cast<float*>(ctx->pinned_scratch)) : *static_cast<double*>(ctx->pinned_scratch);
+  });
+}
+gadcu_status gadcu_value_release(gadcu_value* v) {
+  if (v && v->data) { v->data->release(); v->data = nullptr; }
+  return GADCU_OK;
+}
+gadcu_status gadcu_array_random(gadcu_ctx* ctx, gadcu_dtype dt, const gadcu_dim4* dims, uint64_t seed, int normal, double a, double b,
+                                gadcu_array** out) {
+  return guard([&] {
+    ArrayRef arr = new_array(ctx, dt, Dim4(*dims));
+    k::launch_random(ctx, dt, arr->ptr(), arr->elements(), seed, normal != 0, a, b);
+    *out = arr.detach();
+  });
+}
+// net.rs:171-175: `*self += other` after check_equal_dimensions(other, self)
+gadcu_status gadcu_array_add_assign(gadcu_array* self, const gadcu_array* other) {
+  return guard([&] {
+    if (self->dims != other->dims) fail(GADCU_ERR_DIMENSIONS, "add_assign: " + other->dims.str() + " " + self->dims.str());
+    if (self->dtype != other->dtype) fail(GADCU_ERR_TYPE, "add_assign: dtype mismatch");
+    if (self->lazy()) fail(GADCU_ERR_INVALID, "add_assign into a lazy view");
+    k::EwArgs e;
+    e.dt = self->dtype; e.nin = 2; e.in[0] = self->ptr(); e.in[1] = other->ptr(); e.bcast[1] = other->bcast1();
+    if (other->lazy() && !other->bcast1()) {
+      ArrayRef dense = materialize(ArrayRef(const_cast<gadcu_array*>(other), true));
+      e.in[1] = dense->ptr();
+      e.out = self->ptr(); e.n = self->elements();
+      k::launch_ew(self->ctx, k::EwOp::ADD, e);
+      return;
+    }
+    e.out = self->ptr(); e.n = self->elements();
+    k::launch_ew(self->ctx, k::EwOp::ADD, e);
+  });
+}
+// net.rs:177-179: `self * lambda`
+gadcu_status gadcu_array_scale(const gadcu_array* a, double lambda, gadcu_array** out) {
+  return guard([&] {
+    ArrayRef src = materialize(ArrayRef(const_cast<gadcu_array*>(a), true));
+    ArrayRef r = new_array(a->ctx, a->dtype, a->dims, a->is_scalar);
+    k::EwArgs e;
+    e.dt = a->dtype; e.nin = 1; e.in[0] = src->ptr(); e.out = r->ptr(); e.n = a->elements(); e.c = lambda;
+    k::launch_ew(a->ctx, k::EwOp::MULC, e);
+    *out = r.detach();
+  });
+}
+
+// ---- capture ------------------------------------------------------------------------------------
+gadcu_status gadcu_capture_begin(gadcu_ctx* ctx) {
+  return guard([&] {
+    if (ctx->capturing) fail(GADCU_ERR_INVALID, "capture already active");
+    ctx->capture_pool = std::make_shared<Pool>();
+    ctx->capturing = true;
+    cudaError_t err = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed);
+    if (err != cudaSuccess) {
+      ctx->capturing = false;
+      ctx->capture_pool.reset();
+      fail(GADCU_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(err));
+    }
+  });
+}
+gadcu_status gadcu_capture_end(gadcu_ctx* ctx, gadcu_capture** out) {
+  return guard([&] {
+    if (!ctx->capturing) fail(GADCU_ERR_INVALID, "no capture active");
+    auto cap = std::make_unique<gadcu_capture>();
+    cap->ctx = ctx;
+    cap->pool = ctx->capture_pool;
+    ctx->capturing = false;
+    ctx->capture_pool.reset();
+    GADCU_CUDA(cudaStreamEndCapture(ctx->stream, &cap->graph));
+    GADCU_CUDA(cudaGraphInstantiate(&cap->exec, cap->graph, 0));
+    size_t nodes = 0;
+    cudaGraphGetNodes(cap->graph, nullptr, &nodes);
+    cap->launches = nodes;
+    *out = cap.release();
+  });
+}
+gadcu_status gadcu_capture_launch(gadcu_capture* c) {
+  return guard([&] {
+    GADCU_CUDA(cudaGraphLaunch(c->exec, c->ctx->stream));
+    c->ctx->count_launch(c->launches);
+  });
+}
+gadcu_status gadcu_capture_destroy(gadcu_capture* c) {
+  return guard([&] {
+    if (!c) return;
+    cudaStreamSynchronize(c->ctx->stream);
+    if (c->exec) cudaGraphExecDestroy(c->exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    delete c;
+  });
+}
+
+}  // extern "C"

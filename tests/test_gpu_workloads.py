@@ -1,0 +1,221 @@
+"""GPU: the BASELINE.json configurations against the oracle at sizes the oracle finishes in seconds,
+and through size-independent properties at full size."""
+import numpy as np
+import pytest
+
+import gad_b200 as gb
+import programs
+from gad_b200 import workloads as wl
+from helpers import rand, to_np, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- C1 / C2: scalar tapes, one per lane ------------------------------------------------------------
+@pytest.mark.parametrize("n,lanes", [(2, 1), (8, 33), (64, 1000), (64, 4097)])
+def test_batched_rosenbrock_matches_scalar_tape_bit_for_bit(ctx, oracle, n, lanes):
+    """Rosenbrock uses only +, -, *, neg and constants: every op is an exactly rounded IEEE operation,
+    the op order is the tape's, no FMA contraction on either side => f64 results are bit-identical to
+    the reference-order scalar tape run lane by lane on the CPU."""
+    rng = np.random.default_rng(2)
+    x = -1.2 + 2.4 * rng.random((n, lanes))
+    cols = [ctx.array(x[i]) for i in range(n)]
+    g, f, grads, store = wl.rosenbrock_batched_gradients(ctx, cols)
+    of, ograd, _ = oracle.rosenbrock_batch(x, nthreads=4)
+    got = np.stack([to_np(c)[:, 0, 0, 0] for c in grads])
+    assert got.dtype == np.float64
+    assert np.array_equal(got, ograd), f"max ulp {ulp_diff(got, ograd)}"
+    assert np.allclose(got, programs.rosenbrock_grad_closed_form(x), rtol=1e-11, atol=1e-9)
+    fv = to_np(g.force(f))[:, 0, 0, 0]
+    assert np.array_equal(fv, of)
+    assert g.num_nodes() == n + 8 * (n - 1) + 1  # same tape as the scalar Graph1 (569 for N=64)
+    stats = store.program_stats()
+    assert stats["instructions"] > 0 and stats["slots"] > 0
+    # every tracked node has a store entry, as after a scalar sweep
+    assert len(store.ids()) == g.num_nodes()
+
+
+def test_batched_tape_golden_point_and_f32(ctx):
+    cols = [ctx.array(np.array([-1.2, 1.0])), ctx.array(np.array([1.0, 1.0]))]
+    g, f, grads, _ = wl.rosenbrock_batched_gradients(ctx, cols)
+    got = np.stack([to_np(c)[:, 0, 0, 0] for c in grads])
+    assert np.allclose(got[:, 0], [-215.6, -88.0], atol=1e-10)
+    assert np.all(got[:, 1] == 0.0)
+    # analytic ops through the lane interpreter (f32), against the oracle's scalar Eval
+    x = rand((257,), 4, 0.5, 2.0)
+    for name in ["exp", "log", "log1p", "sin", "cos", "tanh", "sigmoid", "reciprocal", "sqrt"]:
+        bg = gb.BatchedGraph1(ctx, 257, gb.F32)
+        v = bg.variable(ctx.array(x))
+        out = getattr(bg, name)(bg.mulc(v, 2))
+        store = bg.evaluate_gradients_once(out.gid(), 1.7)
+        got = to_np(store.get(v.gid()))[:, 0, 0, 0]
+        x64 = x.astype(np.float64) * 2
+        d = {"exp": np.exp(x64), "log": 1 / x64, "log1p": 1 / (1 + x64), "sin": np.cos(x64), "cos": -np.sin(x64),
+             "tanh": 1 - np.tanh(x64) ** 2, "sigmoid": np.exp(-x64) / (1 + np.exp(-x64)) ** 2, "reciprocal": -1 / x64 ** 2,
+             "sqrt": 0.5 / np.sqrt(x64)}[name] * 2 * 1.7
+        assert np.allclose(got, d, rtol=2e-5, atol=1e-6), name
+
+
+def test_batched_select_pow_div_vs_scalar_oracle(ctx, oracle):
+    lanes = 65
+    a, b = rand((lanes,), 1, 0.5, 2.0, np.float64), rand((lanes,), 2, 0.5, 2.0, np.float64)
+    bg = gb.BatchedGraph1(ctx, lanes, gb.F64)
+    va, vb = bg.variable(ctx.array(a)), bg.variable(ctx.array(b))
+    out = bg.add(bg.max(va, vb), bg.mul(bg.div(va, vb), bg.powc(vb, 3)))
+    store = bg.evaluate_gradients_once(out.gid(), 1.0)
+    ga, gb_ = to_np(store.get(va.gid()))[:, 0, 0, 0], to_np(store.get(vb.gid()))[:, 0, 0, 0]
+    for lane in range(lanes):
+        og = oracle.OGraph1()
+        oa, ob = og.variable(np.float64(a[lane])), og.variable(np.float64(b[lane]))
+        oout = og.add(og.max(oa, ob), og.mul(og.div(oa, ob), og.powc(ob, 3)))
+        ost = og.evaluate_gradients_once(oout.gid(), np.float64(1.0))
+        assert ulp_diff(np.float64(ga[lane]), np.float64(ost.get(oa.gid(), like=oa).data())) <= 2
+        assert ulp_diff(np.float64(gb_[lane]), np.float64(ost.get(ob.gid(), like=ob).data())) <= 2
+
+
+# ---- C3: elementwise tape ------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 1000, 2 ** 20 + 3])
+def test_c3_matches_oracle(ctx, oracle, n):
+    x, y = rand((n,), 3, -1.0, 1.0), rand((n,), 4, 0.5, 2.0)
+    z, gx, gy = wl.c3_step(ctx, ctx.array(x), ctx.array(y))
+    oz, ogx, ogy, _, _ = oracle.c3(x, y)
+    assert ulp_diff(to_np(gx).reshape(-1), ogx) <= 4   # 1 + exp(x)*log(y)... d/dx = log(y)*exp(x) + 1
+    assert ulp_diff(to_np(gy).reshape(-1), ogy) <= 4   # d/dy = exp(x) / y
+    terms = np.exp(x.astype(np.float64)) * np.log(y.astype(np.float64)) + x
+    assert abs(z.item() - terms.sum()) <= 8 * np.finfo(np.float32).eps * np.abs(terms).sum()
+    assert abs(oz - terms.sum()) <= 64 * n * np.finfo(np.float32).eps * max(1.0, np.abs(terms).max())
+
+
+def test_c3_full_size_properties(ctx):
+    """n = 64 Mi (BASELINE config 3): too big for the scalar oracle in seconds, so check properties:
+    closed form on a strided sample, seed linearity (x2 is exact in binary), fused == unfused."""
+    n = 64 * 1024 * 1024
+    x = ctx.random((n,), 3, a=-1.0, b=1.0)
+    y = ctx.random((n,), 4, a=0.5, b=2.0)
+    z, gx, gy = wl.c3_step(ctx, x, y)
+    hx, hy = x.numpy().reshape(-1)[:: 4099], y.numpy().reshape(-1)[:: 4099]
+    hgx, hgy = gx.numpy().reshape(-1), gy.numpy().reshape(-1)
+    want_gx = (np.exp(hx.astype(np.float64)) * np.log(hy.astype(np.float64)) + 1.0).astype(np.float32)
+    want_gy = (np.exp(hx.astype(np.float64)) / hy.astype(np.float64)).astype(np.float32)
+    assert ulp_diff(hgx[:: 4099], want_gx) <= 4
+    assert ulp_diff(hgy[:: 4099], want_gy) <= 4
+    # seed linearity: sweep with seed 2.0 == 2 * sweep with seed 1.0, exactly
+    g = gb.Graph1(ctx)
+    vx, vy, zz = wl.c3_forward(g, x, y)
+    s2 = g.evaluate_gradients(zz.gid(), 2.0)
+    assert np.array_equal(s2.get(vx.gid()).numpy().reshape(-1), 2.0 * hgx)
+    del s2
+    # the unfused (reference op sequence) sweep gives the same bits
+    ctx.set_fusion(False)
+    s1 = g.evaluate_gradients_once(zz.gid(), 1.0)
+    ctx.set_fusion(True)
+    assert np.array_equal(s1.get(vy.gid()).numpy().reshape(-1), hgy)
+    assert np.isfinite(z.item())
+
+
+# ---- C4: MLP -------------------------------------------------------------------------------------
+def _mlp_inputs(B, D, L=3, seed=5):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((B, D)).astype(np.float32)
+    Ws = [(rng.standard_normal((D, D)) / np.sqrt(D)).astype(np.float32) for _ in range(L)]
+    bs = [np.full((1, D), 0.01, np.float32) for _ in range(L)]
+    T = rng.standard_normal((B, D)).astype(np.float32)
+    return X, Ws, bs, T
+
+
+def _mlp_reference_f64(X, Ws, bs, T):
+    h = X.astype(np.float64)
+    acts = [h]
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        z = h @ W.astype(np.float64) + b.astype(np.float64)
+        h = np.tanh(z) if l + 1 < len(Ws) else z
+        acts.append(h)
+    delta = T.astype(np.float64) - h
+    loss = np.sum(delta * delta)
+    g = -2.0 * delta
+    gWs, gbs = [None] * len(Ws), [None] * len(Ws)
+    for l in reversed(range(len(Ws))):
+        if l + 1 < len(Ws):
+            g = g * (1 - acts[l + 1] ** 2)
+        gWs[l] = acts[l].T @ g
+        gbs[l] = g.sum(axis=0, keepdims=True)
+        g = g @ Ws[l].astype(np.float64).T
+    return loss, gWs, gbs
+
+
+@pytest.mark.parametrize("B,D", [(8, 4), (64, 32), (256, 128), (512, 256)])
+def test_mlp_step_matches_oracle(ctx, oracle, B, D):
+    X, Ws, bs, T = _mlp_inputs(B, D)
+    loss, gW, gb_ = wl.mlp_step(ctx, ctx.array(X), [ctx.array(w) for w in Ws], [ctx.array(b) for b in bs], ctx.array(T))
+    oloss, ogW, ogb, _ = oracle.mlp_step(X, Ws, bs, T, nthreads=8)
+    rloss, rgW, rgb = _mlp_reference_f64(X, Ws, bs, T)
+    # both the CUDA path and the oracle sit within f32 rounding of the f64 reference; the CUDA path may
+    # not be further from it than a few times the oracle's own error
+    assert abs(loss.item() - rloss) <= 1e-5 * abs(rloss)
+    assert abs(oloss - rloss) <= 1e-4 * abs(rloss)
+    for l in range(3):
+        a, o, r = to_np(gW[l])[:, :, 0, 0].astype(np.float64), ogW[l].astype(np.float64), rgW[l]
+        scale = np.max(np.abs(r))
+        assert np.max(np.abs(a - r)) <= 2e-5 * scale * np.sqrt(B), (l, np.max(np.abs(a - r)), scale)
+        assert np.max(np.abs(a - r)) <= 8 * np.max(np.abs(o - r)) + 1e-6 * scale
+        a, r = to_np(gb_[l])[:, :, 0, 0].astype(np.float64), rgb[l]
+        assert np.max(np.abs(a - r)) <= 2e-5 * np.max(np.abs(r)) * np.sqrt(B)
+
+
+def test_mlp_sharded_rows_sum_to_the_full_batch(ctx):
+    """The data-parallel seam: gradients of row shards add up to the full-batch gradient."""
+    B, D = 256, 64
+    X, Ws, bs, T = _mlp_inputs(B, D)
+    dW, db = [ctx.array(w) for w in Ws], [ctx.array(b) for b in bs]
+    loss, gW, gb_ = wl.mlp_step(ctx, ctx.array(X), dW, db, ctx.array(T))
+    full = to_np(gW[0])
+    parts, lsum = None, 0.0
+    for r in range(4):
+        rows = slice(r * B // 4, (r + 1) * B // 4)
+        l, gWr, _ = wl.mlp_step(ctx, ctx.array(X[rows]), dW, db, ctx.array(T[rows]))
+        lsum += l.item()
+        if parts is None:
+            parts = gWr[0]
+        else:
+            parts.add_assign(gWr[0])
+    assert np.allclose(to_np(parts), full, rtol=1e-4, atol=1e-5 * np.max(np.abs(full)))
+    assert abs(lsum - loss.item()) <= 1e-5 * abs(loss.item())
+
+
+def test_mlp_hvp_matches_finite_difference_of_gradients(ctx):
+    """C5 (GraphN, reverse-over-reverse): H v ~ (grad(W + eps v) - grad(W - eps v)) / 2 eps."""
+    B, D = 32, 16
+    X, Ws, bs, T = _mlp_inputs(B, D)
+    rng = np.random.default_rng(10)
+    vs = [rng.standard_normal((D, D)).astype(np.float32) for _ in range(3)]
+    dX, dT, db = ctx.array(X), ctx.array(T), [ctx.array(b) for b in bs]
+    hv, loss, nodes = wl.mlp_hvp(ctx, dX, [ctx.array(w) for w in Ws], db, dT, [ctx.array(v) for v in vs])
+    assert nodes > 19  # the recorded backward passes grew the tape
+    eps = 1e-2
+    _, gp, _ = _mlp_reference_f64(X, [w + eps * v for w, v in zip(Ws, vs)], bs, T)
+    _, gm, _ = _mlp_reference_f64(X, [w - eps * v for w, v in zip(Ws, vs)], bs, T)
+    for l in range(3):
+        fd = (gp[l] - gm[l]) / (2 * eps)
+        got = to_np(hv[l])[:, :, 0, 0]
+        assert np.max(np.abs(got - fd)) <= 2e-2 * np.max(np.abs(fd)) + 1e-3
+
+
+# ---- CUDA-graph capture --------------------------------------------------------------------------
+def test_captured_step_replays_bit_identically(ctx):
+    n = 100_003
+    x, y = ctx.array(rand((n,), 3, -1, 1)), ctx.array(rand((n,), 4, 0.5, 2.0))
+    z0, gx0, gy0 = wl.c3_step(ctx, x, y)  # eager (also warms the allocator)
+    want_gx, want_gy, want_z = gx0.numpy(), gy0.numpy(), z0.item()
+    with gb.Capture(ctx) as cap:
+        z, gx, gy = wl.c3_step(ctx, x, y)
+    for _ in range(3):
+        cap.launch()
+    ctx.synchronize()
+    assert np.array_equal(gx.numpy(), want_gx) and np.array_equal(gy.numpy(), want_gy)
+    assert z.item() == want_z
+    # new inputs in the same buffers: the replay recomputes from them
+    x.upload(np.ascontiguousarray(rand((n,), 30, -1, 1)))
+    ctx.synchronize()
+    cap.launch()
+    z1, gx1, gy1 = wl.c3_step(ctx, x, y)
+    assert np.array_equal(gx.numpy(), gx1.numpy())
