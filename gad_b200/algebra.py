@@ -135,6 +135,10 @@ class Context:
     def set_fusion(self, fuse: bool) -> None:
         _check(self.lib.gadcu_ctx_set_fusion(self.handle, int(fuse)))
 
+    def set_strict_reference(self, strict: bool) -> None:
+        """True: reproduce the reference's matmul VJP for transposed operands as is."""
+        _check(self.lib.gadcu_ctx_set_strict_reference(self.handle, int(strict)))
+
     @property
     def stream(self) -> int:
         return int(self.lib.gadcu_ctx_stream(self.handle) or 0)
@@ -504,10 +508,12 @@ class _DeviceAlgebra:
 
     # -- CoreAlgebra
     def variable(self, data) -> Value:
-        return self._call(self.lib.gadcu_variable, self._array(data).handle)
+        arr = self._array(data)  # keep the handle alive across the call
+        return self._call(self.lib.gadcu_variable, arr.handle)
 
     def constant(self, data) -> Value:
-        return self._call(self.lib.gadcu_constant, self._array(data).handle)
+        arr = self._array(data)
+        return self._call(self.lib.gadcu_constant, arr.handle)
 
     def add(self, a, b): return self._b("add", a, b)
 
@@ -594,12 +600,14 @@ class Graph1(_DeviceAlgebra):
 
     def evaluate_gradients(self, gid: GradientId, gradient) -> Store:  # graph.rs:263-274
         h = C.c_void_p()
-        _check(self.lib.gadcu_evaluate_gradients(self.handle, gid.arena, gid.index, self._seed(gradient).handle, 0, C.byref(h)))
+        seed = self._seed(gradient)  # keep the handle alive across the call
+        _check(self.lib.gadcu_evaluate_gradients(self.handle, gid.arena, gid.index, seed.handle, 0, C.byref(h)))
         return Store(self.ctx, h, values=False)
 
     def evaluate_gradients_once(self, gid: GradientId, gradient) -> Store:  # graph.rs:279-290
         h = C.c_void_p()
-        _check(self.lib.gadcu_evaluate_gradients(self.handle, gid.arena, gid.index, self._seed(gradient).handle, 1, C.byref(h)))
+        seed = self._seed(gradient)
+        _check(self.lib.gadcu_evaluate_gradients(self.handle, gid.arena, gid.index, seed.handle, 1, C.byref(h)))
         return Store(self.ctx, h, values=False)
 
     def make_node(self, data: CuArray, inputs: Sequence[Value], vjp) -> Value:

@@ -101,6 +101,7 @@ struct gadcu_ctx {
   std::shared_ptr<gadcu::Pool> capture_pool;  // non-null while capturing
   bool capturing = false;
   bool fuse = true;
+  bool strict_reference = false;  // reproduce the reference's matmul VJP for transposed operands as is
   std::atomic<uint64_t> launches{0};
   void* pinned_scratch = nullptr;  // 4 KiB pinned staging for scalar reads
   void* dev_scratch = nullptr;     // reduction partials

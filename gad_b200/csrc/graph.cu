@@ -533,28 +533,44 @@ void GraphAlgebra::vjp(const Node& n, Algebra& ga, Store& store, const Value& g)
       return;
     }
     case Op::MATMUL: {  // matrix.rs:164-176
+      // Reference: dA = matmul(G, B, p1, p2^T), dB = matmul(A, G, p1^T, p2). These are the correct
+      // adjoints exactly when the differentiated operand is itself not transposed;
+      // otherwise the reference returns a Dimensions error (or, for square matrices, the transpose
+      // of the adjoint). Unless ctx->strict_reference is set, a transposed operand gets the correct
+      // adjoint instead — dA = op2(B) G^T, dB = G^T op1(A) — which is what lets GraphN differentiate
+      // through the recorded backward GEMMs (BASELINE config C5). Identical where the reference is valid.
       const Value &v1 = n.saved[0], &v2 = n.saved[1];
+      const bool fix1 = n.p1.transposed && !ctx->strict_reference;
+      const bool fix2 = n.p2.transposed && !ctx->strict_reference;
+      const MatProp T{true, false};
       if (v1.id.some()) {
+        // operands and props of the product that yields dA
+        const Value& lhs = fix1 ? v2 : g;
+        const Value& rhs = fix1 ? g : v2;
+        const MatProp pl = fix1 ? n.p2 : n.p1, pr = fix1 ? T : n.p2.transpose();
         if (ev) {
           auto it = store.values.find(v1.id);
           ArrayRef cur;
           if (it != store.values.end()) cur = std::move(it->second.data);
-          store.values[v1.id] = Value(ev->matmul_acc(std::move(cur), g.data, v2.data, n.p1, n.p2.transpose()));
+          store.values[v1.id] = Value(ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr));
         } else {
-          Value c2 = ga.link(v2);
-          Value grad = ga.matmul(g, c2, n.p1, n.p2.transpose());
+          Value l = fix1 ? ga.link(lhs) : lhs, r = fix1 ? rhs : ga.link(rhs);
+          Value grad = ga.matmul(l, r, pl, pr);
           store.add_gradient(ga, v1.id, grad);
         }
       }
       if (v2.id.some()) {
+        const Value& lhs = fix2 ? g : v1;
+        const Value& rhs = fix2 ? v1 : g;
+        const MatProp pl = fix2 ? T : n.p1.transpose(), pr = fix2 ? n.p1 : n.p2;
         if (ev) {
           auto it = store.values.find(v2.id);
           ArrayRef cur;
           if (it != store.values.end()) cur = std::move(it->second.data);
-          store.values[v2.id] = Value(ev->matmul_acc(std::move(cur), v1.data, g.data, n.p1.transpose(), n.p2));
+          store.values[v2.id] = Value(ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr));
         } else {
-          Value c1 = ga.link(v1);
-          Value grad = ga.matmul(c1, g, n.p1.transpose(), n.p2);
+          Value l = fix2 ? lhs : ga.link(lhs), r = fix2 ? ga.link(rhs) : rhs;
+          Value grad = ga.matmul(l, r, pl, pr);
           store.add_gradient(ga, v2.id, grad);
         }
       }

@@ -160,6 +160,10 @@ gadcu_status gadcu_ctx_set_fusion(gadcu_ctx* ctx, int fuse) {
   ctx->fuse = fuse != 0;
   return GADCU_OK;
 }
+gadcu_status gadcu_ctx_set_strict_reference(gadcu_ctx* ctx, int strict) {
+  ctx->strict_reference = strict != 0;
+  return GADCU_OK;
+}
 gadcu_status gadcu_ctx_memory_stats(gadcu_ctx* ctx, uint64_t* in_use, uint64_t* reserved, uint64_t* launches) {
   std::lock_guard<std::mutex> lk(ctx->pool->mu);
   if (in_use) *in_use = ctx->pool->in_use;

@@ -87,6 +87,12 @@ GADCU_API void* gadcu_ctx_stream(gadcu_ctx* ctx); /* cudaStream_t */
 /* fuse != 0 (default): the Graph1 sweep runs each VJP + gradient accumulation as one kernel;
  * 0: one kernel per primitive, exactly the reference's op sequence (bit-identical results). */
 GADCU_API gadcu_status gadcu_ctx_set_fusion(gadcu_ctx* ctx, int fuse);
+/* The reference's matmul VJP (gad/src/matrix.rs:164-176) is the correct adjoint only for operands that
+ * are not themselves transposed; for a transposed operand it yields a Dimensions error (or the
+ * transposed adjoint when square). strict != 0 reproduces that as is; the default (0) computes the
+ * correct adjoint in those cases, which GraphN needs to differentiate through recorded backward
+ * GEMMs (Hessian-vector products). Identical wherever the reference formula is valid. */
+GADCU_API gadcu_status gadcu_ctx_set_strict_reference(gadcu_ctx* ctx, int strict);
 GADCU_API gadcu_status gadcu_ctx_memory_stats(gadcu_ctx* ctx, uint64_t* bytes_in_use, uint64_t* bytes_reserved,
                                               uint64_t* kernel_launches);
 

@@ -82,8 +82,10 @@ def test_unary(ctx, oracle, op, shape, dt):
     r = run_both(ctx, oracle, lambda g, v: getattr(g, op)(v[0]), [x], direction_seed)
     ulps = 0 if op in EXACT_UNARY else 4
     assert_close(r["fwd"], r["ofwd"], ulps)
-    # a VJP chains up to 5 rounded ops through a libm value: allow the libm slack to propagate
-    assert_close(r["grads"][0], r["ograds"][0], 0 if op in EXACT_UNARY else 16)
+    # A VJP chains up to 5 rounded ops through a libm value. tanh's (1 - t^2) and sigmoid's c(1 - c)
+    # cancel: a 4-ulp difference in t is amplified by 2t^2/(1-t^2) (x26 at x=2), so their budget is wider.
+    budget = {"tanh": 512, "sigmoid": 128}.get(op, 16)
+    assert_close(r["grads"][0], r["ograds"][0], 0 if op in EXACT_UNARY else budget)
 
 
 @pytest.mark.parametrize("dt", ["f32", "f64"])
@@ -131,7 +133,18 @@ def test_shape_ops(ctx, oracle, dt):
         r = run_both(ctx, oracle, build, [x], direction_seed)
         assert_close(r["fwd"], r["ofwd"], 0)
         assert_close(r["grads"][0], r["ograds"][0], 0)
-    for vshape, rd in [((1, 3), (4, 3)), ((4, 1), (4, 3)), ((1,), (4, 3)), ((2, 1, 2), (4, 3, 2)), ((1, 300), (200, 300))]:
+    # tiling a non-singleton axis has no valid VJP in the reference (sum_as(g, vdims) rejects it,
+    # array.rs:159-170): both sides must report Dimensions from the sweep
+    g, og = gb.Graph1(ctx), oracle.OGraph1()
+    v = rand((2, 1, 2), 8, dtype=DT[dt])
+    t, ot = g.tile_as(g.variable(v), (4, 3, 2)), og.tile_as(og.variable(v), (4, 3, 2))
+    assert np.array_equal(to_np(t), to_np(ot))
+    with pytest.raises(gb.DimensionsError):
+        g.evaluate_gradients_once(t.gid(), np.ones((4, 3, 2), DT[dt]))
+    with pytest.raises(oracle.OracleError) as e:
+        og.evaluate_gradients_once(ot.gid(), np.ones((4, 3, 2), DT[dt]))
+    assert e.value.kind == "Dimensions"
+    for vshape, rd in [((1, 3), (4, 3)), ((4, 1), (4, 3)), ((1,), (4, 3)), ((1, 1, 2), (4, 3, 2)), ((1, 300), (200, 300))]:
         v = rand(vshape, 8, dtype=DT[dt])
         r = run_both(ctx, oracle, lambda g, vv: g.tile_as(vv[0], rd), [v], direction_seed)
         assert_close(r["fwd"], r["ofwd"], 0)
@@ -212,13 +225,35 @@ def test_matmul_transposed_and_batched_forward(ctx, oracle):
     # the reference's matmul VJP with a transposed operand is dimensionally invalid: same error
     g, og = gb.Graph1(ctx), oracle.OGraph1()
     a, b = rand((3, 4), 1), rand((3, 5), 2)
-    c = g.matmul(g.variable(a), g.variable(b), gb.MatProp(True), gb.MatProp())
+    va, vb = g.variable(a), g.variable(b)
+    c = g.matmul(va, vb, gb.MatProp(True), gb.MatProp())
     oc = og.matmul(og.variable(a), og.variable(b), gb.MatProp(True), gb.MatProp())
-    with pytest.raises(gb.DimensionsError):
-        g.evaluate_gradients_once(c.gid(), np.ones((4, 5), np.float32))
+    ctx.set_strict_reference(True)
+    try:
+        with pytest.raises(gb.DimensionsError):
+            g.evaluate_gradients(c.gid(), np.ones((4, 5), np.float32))
+    finally:
+        ctx.set_strict_reference(False)
     with pytest.raises(oracle.OracleError) as e:
         og.evaluate_gradients_once(oc.gid(), np.ones((4, 5), np.float32))
     assert e.value.kind == "Dimensions"
+    # default mode: the correct adjoints (C = A^T B: dA = B G^T, dB = A G), against f64 numpy,
+    # for every transposition pattern
+    for t1, t2 in [(True, False), (False, True), (True, True), (False, False)]:
+        sa, sb = ((3, 4) if t1 else (4, 3)), ((5, 3) if t2 else (3, 5))
+        a, b = rand(sa, 5, -1, 1), rand(sb, 6, -1, 1)
+        g = gb.Graph1(ctx)
+        va, vb = g.variable(a), g.variable(b)
+        c = g.matmul(va, vb, gb.MatProp(t1), gb.MatProp(t2))
+        seed = rand((4, 5), 7, -1, 1)
+        store = g.evaluate_gradients_once(c.gid(), seed)
+        A, B, G = a.astype(np.float64), b.astype(np.float64), seed.astype(np.float64)
+        opA, opB = (A.T if t1 else A), (B.T if t2 else B)
+        dA = G @ opB.T
+        dB = opA.T @ G
+        dA, dB = (dA.T if t1 else dA), (dB.T if t2 else dB)
+        assert np.allclose(to_np(store.get(va.gid()))[:, :, 0, 0], dA, rtol=1e-5, atol=1e-6), (t1, t2)
+        assert np.allclose(to_np(store.get(vb.gid()))[:, :, 0, 0], dB, rtol=1e-5, atol=1e-6), (t1, t2)
 
 
 @pytest.mark.parametrize("rd", [(1, 3), (4, 1), (1,)])
@@ -272,8 +307,12 @@ def test_large_ragged_elementwise_matches_oracle(ctx, oracle):
     n = 1_000_003
     x, y = rand((n,), 3, -1, 1), rand((n,), 4, 0.5, 2.0)
     r = run_both(ctx, oracle, lambda g, v: g.add(g.mul(g.exp(v[0]), g.log(v[1])), v[0]), [x, y], ones_like_seed)
-    assert_close(r["fwd"], r["ofwd"], 8)
-    assert_close(r["grads"][0], r["ograds"][0], 8)
+    # exp(x)*log(y) + x and its x-derivative exp(x)*log(y) + 1 cancel, so the bound is in terms of the
+    # magnitude of the summands: 4 ulp (libm) on the product plus the rounding of the sum
+    eps = np.finfo(np.float32).eps
+    prod = np.abs(np.exp(x.astype(np.float64)) * np.log(y.astype(np.float64)))
+    assert np.all(np.abs(r["fwd"].reshape(-1).astype(np.float64) - r["ofwd"].reshape(-1)) <= 6 * eps * (prod + np.abs(x)))
+    assert np.all(np.abs(r["grads"][0].reshape(-1).astype(np.float64) - r["ograds"][0].reshape(-1)) <= 6 * eps * (prod + 1.0))
     assert_close(r["grads"][1], r["ograds"][1], 8)
 
 

@@ -26,9 +26,12 @@ def estimate_gradient(ctx, x, direction, eps, f):
     for i in range(flat.size):
         x0 = flat[i]
         flat[i] = x0 + eps
-        y2 = ev.dot(f(ev, ev.constant(flat.reshape(v.shape, order="F"))), d).data().item()
+        # the dot with the direction is taken in f64 on the host so that the difference quotient is
+        # limited by the f32 rounding of f itself, as in the reference's CPU runs
+        dh = np.asarray(direction, dtype=np.float64).reshape(-1, order="F")
+        y2 = float(np.dot(to_np(f(ev, ev.constant(flat.reshape(v.shape, order="F")))).reshape(-1, order="F").astype(np.float64), dh))
         flat[i] = x0 - eps
-        y1 = ev.dot(f(ev, ev.constant(flat.reshape(v.shape, order="F"))), d).data().item()
+        y1 = float(np.dot(to_np(f(ev, ev.constant(flat.reshape(v.shape, order="F")))).reshape(-1, order="F").astype(np.float64), dh))
         gflat[i] = (y2 - y1) / (eps + eps)
         flat[i] = x0
     return gflat.reshape(v.shape, order="F")
