@@ -1,11 +1,406 @@
-// gemm_tc.cu — tensor-core GEMM (tcgen05 + TMA, 3xTF32). Placeholder until the kernel lands.
+// gemm_tc.cu — f32 GEMM on the 5th-generation tensor cores: tcgen05.mma (kind::tf32) fed by TMA,
+// accumulators in TMEM, 3xTF32 operand splitting for f32 accuracy. This is the only tensor-core path
+// of the backend: gad's `matmul` forward and its two VJP products dA = G.B^T, dB = A^T.G
+// (gad/src/matrix.rs:153-179), which are >95 % of the MLP step.
+//
+// 3xTF32: every f32 operand x is split (split_tf32_kernel, one HBM pass) into hi = rna_tf32(x) and
+// lo = rna_tf32(x - hi); the product is accumulated in f32 (TMEM) as
+//      A.B  ~=  Ahi.Bhi + Ahi.Blo + Alo.Bhi          (the dropped Alo.Blo term is <= 2^-22 |a||b|)
+// i.e. three tensor-core MMAs per logical product.
+//
+// Kernel shape (v1, one CTA per 128 x BN output tile):
+//   warp 4      TMA producer : per k-block of 32, four bulk tensor copies (Ahi, Alo, Bhi, Blo) into a
+//                              kStages-deep shared-memory ring, completion on an mbarrier (expect_tx)
+//   warp 5      MMA issuer   : one elected thread issues 4 k-steps x 3 tcgen05.mma per k-block into the
+//                              TMEM accumulator, tcgen05.commit releases the ring slot
+//   warps 0-3   epilogue     : tcgen05.ld (32 lanes x 32 columns per warp), optional `C + acc`
+//                              (gradient accumulation fused into the epilogue), coalesced column-major stores
+// Operands are column-major with optional transposition, so each is either K-major or MN-major in
+// UMMA terms; both are fed directly (no transpose pass): the TMA tensor map lays the tile out in the
+// canonical 128-byte-swizzled layout of its major-ness and the smem/instruction descriptors say which.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+
 #include "kernels.h"
 
 namespace gadcu {
 namespace k {
+namespace {
 
-bool gemm_tc_supported(const GemmArgs&) { return false; }
-void launch_gemm_tc(gadcu_ctx*, const GemmArgs&) { fail(GADCU_ERR_UNSUPPORTED, "tensor-core gemm not built"); }
+constexpr int BM = 128;      // UMMA M (cta_group::1)
+constexpr int BK = 32;       // k-block: 32 tf32 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;    // tf32: 32 bytes per instruction
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = 192;
+
+template <int BN> struct Cfg {
+  static constexpr int kStages = BN == 256 ? 2 : 3;
+  static constexpr uint32_t kTileA = BM * BK * 4;       // 16 KiB
+  static constexpr uint32_t kTileB = BN * BK * 4;
+  static constexpr uint32_t kStageBytes = 2 * kTileA + 2 * kTileB;
+  static constexpr uint32_t kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]   (kind::tf32, f32 accumulate)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= uint64_t((addr >> 4) & 0x3FFF);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(layout) << 61;
+  return d;
+}
+
+// Layout of one operand tile in shared memory (rows of 128 bytes, swizzled within 128-byte spans):
+//   K-major  : [rows = MN][32 k], 16-byte chunks swizzled over 8-row groups (SWIZZLE_128B, layout 2),
+//              8-row groups 1024 B apart -> SBO = 1024, k-step (8 k) +32 B inside the row
+//   MN-major : [MN/32 slabs][32 k][32 mn]; for 32-bit operands the only MN-major layout tcgen05 takes is
+//              SWIZZLE_128B_BASE32B (layout 1): 32-byte chunks swizzled over 4-row groups, i.e. an atom
+//              of 32 mn x 4 k = 512 B -> SBO = 512 (next 4 k), LBO = slab = BK*128 B (next 32 mn),
+//              k-step (8 k-rows) +1024 B. The TMA map uses CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B to match.
+struct OperandLayout {
+  uint32_t lbo, sbo, kstep, layout;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                   const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, float* __restrict__ C,
+                   uint32_t M, uint32_t N, uint32_t K, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t accumulate,
+                   OperandLayout la, OperandLayout lb) {
+  using cfg = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bars = smem_base + cfg::kStages * cfg::kStageBytes;  // full[S], empty[S], tmem_full, tmem slot
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (cfg::kStages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * cfg::kStages);
+  const uint32_t tmem_slot = bars + 8u * (2 * cfg::kStages + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + cfg::kStages * cfg::kStageBytes + 8 * (2 * cfg::kStages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const uint32_t num_kb = K / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < cfg::kStages; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&map_ah);
+    tma_prefetch_desc(&map_al);
+    tma_prefetch_desc(&map_bh);
+    tma_prefetch_desc(&map_bl);
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, BN);  // BN f32 accumulator columns (power of two >= 32)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (uint32_t kb = 0; kb < num_kb; kb++) {
+        const int s = kb % cfg::kStages;
+        const uint32_t phase = (kb / cfg::kStages) & 1;
+        mbar_wait(empty_bar(s), phase ^ 1);
+        const uint32_t stage = smem_base + s * cfg::kStageBytes;
+        const uint32_t sa_h = stage, sa_l = stage + cfg::kTileA, sb_h = stage + 2 * cfg::kTileA, sb_l = sb_h + cfg::kTileB;
+        mbar_expect_tx(full_bar(s), cfg::kStageBytes);
+        const int k0 = int(kb * BK);
+        if (a_mn_major) {
+          tma_load_3d(sa_h, &map_ah, full_bar(s), 0, k0, int(m0 / 32));
+          tma_load_3d(sa_l, &map_al, full_bar(s), 0, k0, int(m0 / 32));
+        } else {
+          tma_load_2d(sa_h, &map_ah, full_bar(s), k0, int(m0));
+          tma_load_2d(sa_l, &map_al, full_bar(s), k0, int(m0));
+        }
+        if (b_mn_major) {
+          tma_load_3d(sb_h, &map_bh, full_bar(s), 0, k0, int(n0 / 32));
+          tma_load_3d(sb_l, &map_bl, full_bar(s), 0, k0, int(n0 / 32));
+        } else {
+          tma_load_2d(sb_h, &map_bh, full_bar(s), k0, int(n0));
+          tma_load_2d(sb_l, &map_bl, full_bar(s), k0, int(n0));
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b=TF32 [7,10)/[10,13),
+      // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+                             (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+      for (uint32_t kb = 0; kb < num_kb; kb++) {
+        const int s = kb % cfg::kStages;
+        const uint32_t phase = (kb / cfg::kStages) & 1;
+        mbar_wait(full_bar(s), phase);
+        tc_fence_after();
+        const uint32_t stage = smem_base + s * cfg::kStageBytes;
+        const uint32_t sa_h = stage, sa_l = stage + cfg::kTileA, sb_h = stage + 2 * cfg::kTileA, sb_l = sb_h + cfg::kTileB;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; k++) {
+          const uint64_t dah = make_smem_desc(sa_h + k * la.kstep, la.lbo, la.sbo, la.layout);
+          const uint64_t dal = make_smem_desc(sa_l + k * la.kstep, la.lbo, la.sbo, la.layout);
+          const uint64_t dbh = make_smem_desc(sb_h + k * lb.kstep, lb.lbo, lb.sbo, lb.layout);
+          const uint64_t dbl = make_smem_desc(sb_l + k * lb.kstep, lb.lbo, lb.sbo, lb.layout);
+          // small terms first, then the leading product
+          umma_tf32(tmem_base, dal, dbh, idesc, (kb | uint32_t(k)) != 0);
+          umma_tf32(tmem_base, dah, dbl, idesc, 1);
+          umma_tf32(tmem_base, dah, dbh, idesc, 1);
+        }
+        umma_commit(empty_bar(s));  // frees the ring slot once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);   // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global (column-major: lanes = consecutive rows) =====
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    __syncwarp();
+    const uint32_t row = m0 + warp * 32 + lane;
+    float* crow = C + row;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(c), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        float* p = crow + size_t(n0 + c + j) * M;
+        float v = __uint_as_float(r[j]);
+        if (accumulate) v = *p + v;  // store.rs:52 `current + new`, fused into the epilogue
+        *p = v;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// hi = rna_tf32(x), lo = rna_tf32(x - hi); one pass, 128-bit accesses
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo,
+                                                         uint64_t nvec) {
+  const uint64_t stride = uint64_t(gridDim.x) * 256;
+  for (uint64_t i = uint64_t(blockIdx.x) * 256 + threadIdx.x; i < nvec; i += stride) {
+    const float4 v = __ldcs(x + i);
+    float4 h, l;
+    uint32_t t;
+#define GADCU_SPLIT(c)                                                      \
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.c));                     \
+  h.c = __uint_as_float(t);                                                 \
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.c - h.c));               \
+  l.c = __uint_as_float(t);
+    GADCU_SPLIT(x) GADCU_SPLIT(y) GADCU_SPLIT(z) GADCU_SPLIT(w)
+#undef GADCU_SPLIT
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  if (!fn) fail(GADCU_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  return fn;
+}
+
+// Tensor map for one operand whose stored matrix is column-major with leading dimension `ld`.
+//   mn_major: element (mn, k) at mn + ld*k  -> 3-D view [32, K, MN/32], box {32, BK, rows/32}
+//   k_major : element (mn, k) at k + ld*mn  -> 2-D view [K, MN],        box {32, rows}
+CUtensorMap make_map(const float* base, bool mn_major, uint64_t mn, uint64_t kdim, uint64_t ld, uint32_t rows,
+                     CUtensorMapSwizzle mn_swizzle = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) {
+  CUtensorMap map;
+  CUresult rc;
+  if (mn_major) {
+    cuuint64_t dims[3] = {32, kdim, mn / 32};
+    cuuint64_t strides[2] = {ld * 4, 128};
+    cuuint32_t box[3] = {32, BK, rows / 32};
+    cuuint32_t estr[3] = {1, 1, 1};
+    rc = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, mn_swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[2] = {kdim, mn};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2] = {BK, rows};
+    cuuint32_t estr[2] = {1, 1};
+    rc = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (rc != CUDA_SUCCESS) fail(GADCU_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(rc)));
+  return map;
+}
+
+void split(gadcu_ctx* ctx, const float* x, float* hi, float* lo, uint64_t n) {
+  const uint64_t nvec = n / 4;
+  uint64_t blocks = (nvec + 255) / 256;
+  const uint64_t cap = uint64_t(ctx->sm_count) * 8;
+  if (blocks > cap) blocks = cap;
+  split_tf32_kernel<<<unsigned(blocks), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi),
+                                                              reinterpret_cast<float4*>(lo), nvec);
+  ctx->count_launch();
+}
+
+int tc_mode() {  // GADCU_GEMM=simt disables the tensor-core path (A/B testing)
+  static int mode = [] {
+    const char* e = getenv("GADCU_GEMM");
+    return (e && std::string(e) == "simt") ? 0 : 1;
+  }();
+  return mode;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const GemmArgs& g) {
+  if (!tc_mode()) return false;
+  if (g.dt != GADCU_F32 || g.batch != 1) return false;
+  if (g.M % 128 || g.N % 128 || g.K % BK || g.K == 0) return false;
+  // the stored matrices must tile exactly (whole-matrix operands, 16-byte aligned rows)
+  const uint64_t a_rows = g.ta ? g.K : g.M, b_rows = g.tb ? g.N : g.K;
+  if (g.lda != a_rows || g.ldb != b_rows) return false;
+  if ((reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.B) | reinterpret_cast<uintptr_t>(g.C)) & 15) return false;
+  if (g.M >= (1ull << 31) || g.N >= (1ull << 31) || g.K >= (1ull << 31)) return false;
+  return true;
+}
+
+void launch_gemm_tc(gadcu_ctx* ctx, const GemmArgs& g) {
+  const uint64_t a_elems = g.M * g.K, b_elems = g.K * g.N;
+  ArrayRef tmp = new_array(ctx, GADCU_F32, Dim4(2 * (a_elems + b_elems)));
+  float* ah = static_cast<float*>(tmp->ptr());
+  float* al = ah + a_elems;
+  float* bh = al + a_elems;
+  float* bl = bh + b_elems;
+  split(ctx, static_cast<const float*>(g.A), ah, al, a_elems);
+  split(ctx, static_cast<const float*>(g.B), bh, bl, b_elems);
+
+  const bool a_mn = !g.ta;  // stored [M,K] col-major: M contiguous
+  const bool b_mn = g.tb;   // stored [N,K] col-major: N contiguous
+  const int BN = (g.N % 256 == 0 && (g.M / BM) * (g.N / 256) >= uint64_t(ctx->sm_count)) ? 256 : 128;
+  const OperandLayout mn_layout{BK * 128u, 512u, 1024u, 1u};
+  const OperandLayout k_layout{16u, 1024u, UMMA_K * 4u, 2u};
+  const CUtensorMapSwizzle mn_swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  const OperandLayout la = a_mn ? mn_layout : k_layout, lb = b_mn ? mn_layout : k_layout;
+  CUtensorMap mah = make_map(ah, a_mn, g.M, g.K, g.lda, BM, mn_swz), mal = make_map(al, a_mn, g.M, g.K, g.lda, BM, mn_swz);
+  CUtensorMap mbh = make_map(bh, b_mn, g.N, g.K, g.ldb, BN, mn_swz), mbl = make_map(bl, b_mn, g.N, g.K, g.ldb, BN, mn_swz);
+  dim3 grid(unsigned(g.M / BM), unsigned(g.N / BN));
+  if (BN == 256) {
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(gemm_tf32x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmem); });
+    gemm_tf32x3_kernel<256><<<grid, kThreads, Cfg<256>::kSmem, ctx->stream>>>(mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M),
+                                                                             uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb);
+  } else {
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(gemm_tf32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::kSmem); });
+    gemm_tf32x3_kernel<128><<<grid, kThreads, Cfg<128>::kSmem, ctx->stream>>>(mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M),
+                                                                             uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb);
+  }
+  ctx->count_launch();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) fail(GADCU_ERR_CUDA, std::string("gemm_tf32x3 launch: ") + cudaGetErrorString(err));
+}
 
 }  // namespace k
 }  // namespace gadcu

@@ -1,0 +1,62 @@
+"""GPU: the tcgen05 + TMA 3xTF32 GEMM against f64 numpy, all four major-ness combinations (the forward
+product, dA = G.B^T and dB = A^T.G feed K-major / MN-major operands directly), accumulate epilogue."""
+import numpy as np
+import pytest
+
+import gad_b200 as gb
+from helpers import to_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, M, N, K, t1, t2, seed=0):
+    rng = np.random.default_rng(seed)
+    sa, sb = ((K, M) if t1 else (M, K)), ((N, K) if t2 else (K, N))
+    a = rng.standard_normal(sa).astype(np.float32)
+    b = rng.standard_normal(sb).astype(np.float32)
+    ev = gb.Eval(ctx)
+    got = to_np(ev.matmul(ev.constant(a), ev.constant(b), gb.MatProp(t1), gb.MatProp(t2)))[:, :, 0, 0].astype(np.float64)
+    A, B = a.astype(np.float64), b.astype(np.float64)
+    opA, opB = (A.T if t1 else A), (B.T if t2 else B)
+    want = opA @ opB
+    # tolerance (DESIGN.md "GEMM numerics"): 3xTF32 drops a_lo.b_lo and rounds the two lo parts,
+    # <= 3 * 2^-22 |a||b| per product; the f32 accumulator in TMEM is rounded once per tcgen05.mma, i.e.
+    # 3 * K/8 times, each <= 2^-23 of the running sum (the tensor core truncates). Both are bounded by
+    # multiples of S = sum_k |a_k||b_k|; a plain f32 GEMM carries K * 2^-24 S from its accumulation alone.
+    S = np.abs(opA) @ np.abs(opB)
+    bound = (2.0 ** -20 + 3 * (K / 8) * 2.0 ** -23) * S
+    err = np.abs(got - want)
+    assert np.all(err <= bound), (M, N, K, t1, t2, float(err.max()), float((err / bound).max()))
+    # and the typical error stays at f32 level: rms(err / S) within 2^-20 (single-pass TF32 would be ~2^-12)
+    assert float(np.sqrt(np.mean((err / S) ** 2))) <= 2.0 ** -20
+    return float((err / (2.0 ** -20 * S)).max())
+
+
+@pytest.mark.parametrize("t1,t2", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (256, 128, 64), (128, 256, 96), (384, 512, 160), (1024, 1024, 1024)])
+def test_gemm_tc_matches_f64(ctx, M, N, K, t1, t2):
+    _check(ctx, M, N, K, t1, t2)
+
+
+def test_gemm_tc_is_far_more_accurate_than_single_tf32(ctx):
+    """3xTF32 stays within a few 2^-20 of the |a||b| sum at K=2048; a single-pass TF32 product is ~2^-11."""
+    worst = _check(ctx, 512, 512, 2048, False, False, seed=3)
+    assert worst < 8.0
+
+
+def test_gemm_tc_accumulate_epilogue(ctx):
+    """dW accumulation `current + new` fused into the GEMM epilogue: two contributions into one gradient."""
+    rng = np.random.default_rng(1)
+    M = N = K = 256
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = rng.standard_normal((K, N)).astype(np.float32)
+    g = gb.Graph1(ctx)
+    vw = g.variable(w)
+    cx = g.constant(x)
+    y = g.add(g.matmul_nn(cx, vw), g.matmul_nn(cx, vw))  # w used twice: second dW accumulates
+    seed = rng.standard_normal((M, N)).astype(np.float32)
+    store = g.evaluate_gradients_once(y.gid(), seed)
+    got = to_np(store.get(vw.gid()))[:, :, 0, 0].astype(np.float64)
+    want = 2.0 * (x.astype(np.float64).T @ seed.astype(np.float64))
+    bound = 2.0 ** -19 * (np.abs(x.astype(np.float64)).T @ np.abs(seed.astype(np.float64)))
+    assert np.all(np.abs(got - want) <= bound)

@@ -163,7 +163,7 @@ def test_mlp_step_matches_oracle(ctx, oracle, B, D):
         a, o, r = to_np(gW[l])[:, :, 0, 0].astype(np.float64), ogW[l].astype(np.float64), rgW[l]
         scale = np.max(np.abs(r))
         assert np.max(np.abs(a - r)) <= 2e-5 * scale * np.sqrt(B), (l, np.max(np.abs(a - r)), scale)
-        assert np.max(np.abs(a - r)) <= 8 * np.max(np.abs(o - r)) + 1e-6 * scale
+        assert np.max(np.abs(a - r)) <= 8 * np.max(np.abs(o - r)) + 2e-6 * scale  # tcgen05 accumulates with truncation
         a, r = to_np(gb_[l])[:, :, 0, 0].astype(np.float64), rgb[l]
         assert np.max(np.abs(a - r)) <= 2e-5 * np.max(np.abs(r)) * np.sqrt(B)
 
