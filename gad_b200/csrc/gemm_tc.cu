@@ -20,6 +20,7 @@
 // canonical 128-byte-swizzled layout of its major-ness and the smem/instruction descriptors say which.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -268,6 +269,249 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
   }
 }
 
+
+// =================================================================================================
+// v2: persistent CTA-pair kernel (cta_group::2). One cluster of two CTAs owns a 256 x 256 output tile:
+// CTA r holds rows [128r, 128r+128) of the A tile and columns [128r, 128r+128) of the B tile, so each
+// SM loads half of what two independent 128 x 256 CTAs would (42.7 B/clk/SM of L2->SM traffic at full
+// tensor rate instead of 62.5 — the v1 kernel was pinned at the ~6.3 KB/clk chip-wide L2 output cap).
+// The accumulator (128 lanes x 256 f32 columns per CTA) is double-buffered over all 512 TMEM columns:
+// the epilogue of tile i drains one buffer while the MMAs of tile i+1 fill the other.
+//   warp 0      TMA producer (both CTAs; completion bytes land on the LEADER's full barrier)
+//   warp 1      MMA issuer   (leader CTA only; tcgen05.commit multicasts to both CTAs' barriers)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue     (both CTAs, each drains its own 128 accumulator lanes)
+// Tiles are handed out statically, cluster c takes tiles c, c+G, c+2G, ... in an order that walks
+// `band_m` tile-rows at a time (a wave of 74 clusters covers ~8 x 9 tiles: operand slices are shared
+// through L2 while they are hot).
+constexpr int kThreads2 = 256;
+constexpr uint32_t kAccCols = 256;
+
+template <int BKT, int S> struct Cfg2 {
+  static constexpr uint32_t kTile = 128 * BKT * 4;
+  static constexpr uint32_t kStageBytes = 4 * kTile;  // A_hi, A_lo, B_hi, B_lo (this CTA's halves)
+  static constexpr uint32_t kSmem = S * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in both CTAs of the pair once the MMAs issued so far complete
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(uint16_t(3))
+               : "memory");
+}
+
+struct TileSched {
+  uint32_t num_mt, num_nt, total, band_m;
+  __device__ __forceinline__ void decode(uint32_t t, uint32_t& mt, uint32_t& nt) const {
+    const uint32_t band_size = band_m * num_nt;
+    const uint32_t band = t / band_size, r = t - band * band_size;
+    const uint32_t rows = min(band_m, num_mt - band * band_m);
+    nt = r / rows;
+    mt = band * band_m + (r - nt * rows);
+  }
+};
+
+template <int BKT, int S>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                        const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, float* __restrict__ C,
+                        uint32_t M, uint32_t N, uint32_t K, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t accumulate,
+                        OperandLayout la, OperandLayout lb, uint32_t band_m) {
+  using cfg = Cfg2<BKT, S>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bars = smem_base + S * cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + S * cfg::kStageBytes + 8 * (2 * S + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const uint32_t num_kb = K / BKT;
+  TileSched sched{M / 256, N / 256, (M / 256) * (N / 256), band_m};
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; s++) {
+      mbar_init(full_bar(s), 1);   // the leader's producer arms it with the byte count of both CTAs
+      mbar_init(empty_bar(s), 1);  // one multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 2 * kEpiWarps);  // every epilogue warp of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_ah);
+    tma_prefetch_desc(&map_al);
+    tma_prefetch_desc(&map_bh);
+    tma_prefetch_desc(&map_bl);
+  }
+  if (warp == 2) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / complete_tx
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer: this CTA's halves of the A and B tiles =====
+    if (lane == 0) {
+      uint32_t it = 0;  // k-blocks issued so far (ring position)
+      for (uint32_t t = cluster_id; t < sched.total; t += num_clusters) {
+        uint32_t mt, nt;
+        sched.decode(t, mt, nt);
+        const uint32_t m0 = mt * 256 + rank * 128, n0 = nt * 256 + rank * 128;
+        for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % S;
+          const uint32_t phase = (it / S) & 1;
+          mbar_wait(empty_bar(s), phase ^ 1);
+          const uint32_t stage = smem_base + s * cfg::kStageBytes;
+          const uint32_t sa_h = stage, sa_l = stage + cfg::kTile, sb_h = stage + 2 * cfg::kTile, sb_l = stage + 3 * cfg::kTile;
+          if (rank == 0) mbar_expect_tx(full_bar(s), 2 * cfg::kStageBytes);
+          const uint32_t fb = mapa(full_bar(s), 0);
+          const int k0 = int(kb * BKT);
+          if (a_mn_major) {
+            tma2_load_3d(sa_h, &map_ah, fb, 0, k0, int(m0 / 32));
+            tma2_load_3d(sa_l, &map_al, fb, 0, k0, int(m0 / 32));
+          } else {
+            tma2_load_2d(sa_h, &map_ah, fb, k0, int(m0));
+            tma2_load_2d(sa_l, &map_al, fb, k0, int(m0));
+          }
+          if (b_mn_major) {
+            tma2_load_3d(sb_h, &map_bh, fb, 0, k0, int(n0 / 32));
+            tma2_load_3d(sb_l, &map_bl, fb, 0, k0, int(n0 / 32));
+          } else {
+            tma2_load_2d(sb_h, &map_bh, fb, k0, int(n0));
+            tma2_load_2d(sb_l, &map_bl, fb, k0, int(n0));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+                             (uint32_t(256 >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+      uint32_t it = 0, ti = 0;
+      for (uint32_t t = cluster_id; t < sched.total; t += num_clusters, ti++) {
+        const uint32_t as = ti & 1, use = ti >> 1;
+        mbar_wait(tmem_empty_bar(as), (use & 1) ^ 1);  // both epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kAccCols;
+        for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % S;
+          const uint32_t phase = (it / S) & 1;
+          mbar_wait(full_bar(s), phase);
+          tc_fence_after();
+          const uint32_t stage = smem_base + s * cfg::kStageBytes;
+          const uint32_t sa_h = stage, sa_l = stage + cfg::kTile, sb_h = stage + 2 * cfg::kTile, sb_l = stage + 3 * cfg::kTile;
+#pragma unroll
+          for (int k = 0; k < BKT / UMMA_K; k++) {
+            const uint64_t dah = make_smem_desc(sa_h + k * la.kstep, la.lbo, la.sbo, la.layout);
+            const uint64_t dal = make_smem_desc(sa_l + k * la.kstep, la.lbo, la.sbo, la.layout);
+            const uint64_t dbh = make_smem_desc(sb_h + k * lb.kstep, lb.lbo, lb.sbo, lb.layout);
+            const uint64_t dbl = make_smem_desc(sb_l + k * lb.kstep, lb.lbo, lb.sbo, lb.layout);
+            umma2_tf32(tmem_d, dal, dbh, idesc, (kb | uint32_t(k)) != 0);  // small terms first
+            umma2_tf32(tmem_d, dah, dbl, idesc, 1);
+            umma2_tf32(tmem_d, dah, dbh, idesc, 1);
+          }
+          umma2_commit_mc(empty_bar(s));  // both CTAs' ring slots are free once these MMAs have read them
+        }
+        umma2_commit_mc(tmem_full_bar(as));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: this CTA's 128 accumulator lanes -> global (column-major: lanes = consecutive rows) =====
+    const int q = warp - 4;  // TMEM lane quarter this warp may read
+    const uint32_t te = mapa(tmem_empty_bar(0), 0);
+    uint32_t ti = 0;
+    for (uint32_t t = cluster_id; t < sched.total; t += num_clusters, ti++) {
+      uint32_t mt, nt;
+      sched.decode(t, mt, nt);
+      const uint32_t as = ti & 1, use = ti >> 1;
+      mbar_wait(tmem_full_bar(as), use & 1);
+      tc_fence_after();
+      const uint32_t row = mt * 256 + rank * 128 + q * 32 + lane;
+      float* crow = C + row + size_t(nt) * 256 * M;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * kAccCols;
+#pragma unroll 1
+      for (int c = 0; c < 256; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + uint32_t(c), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          float* p = crow + size_t(c + j) * M;
+          float v = __uint_as_float(r[j]);
+          if (accumulate) v = *p + v;  // store.rs:52 `current + new`, fused into the epilogue
+          *p = v;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(te + 8u * as);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves while the peer can still read this CTA's smem / signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 // hi = rna_tf32(x), lo = rna_tf32(x - hi); one pass, 128-bit accesses
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo,
                                                          uint64_t nvec) {
@@ -309,14 +553,15 @@ EncodeTiledFn encode_fn() {
 // Tensor map for one operand whose stored matrix is column-major with leading dimension `ld`.
 //   mn_major: element (mn, k) at mn + ld*k  -> 3-D view [32, K, MN/32], box {32, BK, rows/32}
 //   k_major : element (mn, k) at k + ld*mn  -> 2-D view [K, MN],        box {32, rows}
-CUtensorMap make_map(const float* base, bool mn_major, uint64_t mn, uint64_t kdim, uint64_t ld, uint32_t rows,
-                     CUtensorMapSwizzle mn_swizzle = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) {
+CUtensorMap make_map(const float* base, bool mn_major, uint64_t mn, uint64_t kdim, uint64_t ld, uint32_t rows, uint32_t bk = BK,
+                     CUtensorMapSwizzle k_swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  const CUtensorMapSwizzle mn_swizzle = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap map;
   CUresult rc;
   if (mn_major) {
     cuuint64_t dims[3] = {32, kdim, mn / 32};
     cuuint64_t strides[2] = {ld * 4, 128};
-    cuuint32_t box[3] = {32, BK, rows / 32};
+    cuuint32_t box[3] = {32, bk, rows / 32};
     cuuint32_t estr[3] = {1, 1, 1};
     rc = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, mn_swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -324,10 +569,10 @@ CUtensorMap make_map(const float* base, bool mn_major, uint64_t mn, uint64_t kdi
   } else {
     cuuint64_t dims[2] = {kdim, mn};
     cuuint64_t strides[1] = {ld * 4};
-    cuuint32_t box[2] = {BK, rows};
+    cuuint32_t box[2] = {bk, rows};
     cuuint32_t estr[2] = {1, 1};
     rc = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, k_swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (rc != CUDA_SUCCESS) fail(GADCU_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(rc)));
@@ -366,6 +611,40 @@ bool gemm_tc_supported(const GemmArgs& g) {
   return true;
 }
 
+namespace {
+
+template <int BKT, int S>
+void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float* al, const float* bh, const float* bl, bool a_mn,
+                 bool b_mn) {
+  // K-major tiles have rows of BKT*4 bytes: 128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B (8-row groups either way)
+  const OperandLayout k_layout = BKT == 32 ? OperandLayout{16u, 1024u, UMMA_K * 4u, 2u} : OperandLayout{16u, 512u, UMMA_K * 4u, 4u};
+  const CUtensorMapSwizzle k_swz = BKT == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const OperandLayout mn_layout{BKT * 128u, 512u, 1024u, 1u};
+  const OperandLayout la = a_mn ? mn_layout : k_layout, lb = b_mn ? mn_layout : k_layout;
+  CUtensorMap mah = make_map(ah, a_mn, g.M, g.K, g.lda, 128, BKT, k_swz), mal = make_map(al, a_mn, g.M, g.K, g.lda, 128, BKT, k_swz);
+  CUtensorMap mbh = make_map(bh, b_mn, g.N, g.K, g.ldb, 128, BKT, k_swz), mbl = make_map(bl, b_mn, g.N, g.K, g.ldb, 128, BKT, k_swz);
+  const uint64_t tiles = (g.M / 256) * (g.N / 256);
+  const uint64_t clusters = std::min<uint64_t>(tiles, uint64_t(ctx->sm_count / 2));
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<BKT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BKT, S>::kSmem);
+  });
+  gemm_tf32x3_pair_kernel<BKT, S><<<unsigned(2 * clusters), kThreads2, Cfg2<BKT, S>::kSmem, ctx->stream>>>(
+      mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M), uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb, 8u);
+}
+
+int pair_variant() {  // GADCU_GEMM_PAIR = off | 32x3 | 16x6 (default 32x3)
+  static int v = [] {
+    const char* e = getenv("GADCU_GEMM_PAIR");
+    if (!e) return 1;
+    const std::string s(e);
+    return s == "off" ? 0 : s == "16x6" ? 2 : s == "16x4" ? 3 : 1;
+  }();
+  return v;
+}
+
+}  // namespace
+
 void launch_gemm_tc(gadcu_ctx* ctx, const GemmArgs& g) {
   const uint64_t a_elems = g.M * g.K, b_elems = g.K * g.N;
   ArrayRef tmp = new_array(ctx, GADCU_F32, Dim4(2 * (a_elems + b_elems)));
@@ -378,24 +657,31 @@ void launch_gemm_tc(gadcu_ctx* ctx, const GemmArgs& g) {
 
   const bool a_mn = !g.ta;  // stored [M,K] col-major: M contiguous
   const bool b_mn = g.tb;   // stored [N,K] col-major: N contiguous
-  const int BN = (g.N % 256 == 0 && (g.M / BM) * (g.N / 256) >= uint64_t(ctx->sm_count)) ? 256 : 128;
-  const OperandLayout mn_layout{BK * 128u, 512u, 1024u, 1u};
-  const OperandLayout k_layout{16u, 1024u, UMMA_K * 4u, 2u};
-  const CUtensorMapSwizzle mn_swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  const OperandLayout la = a_mn ? mn_layout : k_layout, lb = b_mn ? mn_layout : k_layout;
-  CUtensorMap mah = make_map(ah, a_mn, g.M, g.K, g.lda, BM, mn_swz), mal = make_map(al, a_mn, g.M, g.K, g.lda, BM, mn_swz);
-  CUtensorMap mbh = make_map(bh, b_mn, g.N, g.K, g.ldb, BN, mn_swz), mbl = make_map(bl, b_mn, g.N, g.K, g.ldb, BN, mn_swz);
-  dim3 grid(unsigned(g.M / BM), unsigned(g.N / BN));
-  if (BN == 256) {
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(gemm_tf32x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmem); });
-    gemm_tf32x3_kernel<256><<<grid, kThreads, Cfg<256>::kSmem, ctx->stream>>>(mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M),
-                                                                             uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb);
+  if (pair_variant() && g.M % 256 == 0 && g.N % 256 == 0) {
+    switch (pair_variant()) {
+      case 2: launch_pair<16, 6>(ctx, g, ah, al, bh, bl, a_mn, b_mn); break;
+      case 3: launch_pair<16, 4>(ctx, g, ah, al, bh, bl, a_mn, b_mn); break;
+      default: launch_pair<32, 3>(ctx, g, ah, al, bh, bl, a_mn, b_mn); break;
+    }
   } else {
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(gemm_tf32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::kSmem); });
-    gemm_tf32x3_kernel<128><<<grid, kThreads, Cfg<128>::kSmem, ctx->stream>>>(mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M),
-                                                                             uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb);
+    const OperandLayout mn_layout{BK * 128u, 512u, 1024u, 1u};
+    const OperandLayout k_layout{16u, 1024u, UMMA_K * 4u, 2u};
+    const OperandLayout la = a_mn ? mn_layout : k_layout, lb = b_mn ? mn_layout : k_layout;
+    const int BN = (g.N % 256 == 0 && (g.M / BM) * (g.N / 256) >= uint64_t(ctx->sm_count)) ? 256 : 128;
+    CUtensorMap mah = make_map(ah, a_mn, g.M, g.K, g.lda, BM), mal = make_map(al, a_mn, g.M, g.K, g.lda, BM);
+    CUtensorMap mbh = make_map(bh, b_mn, g.N, g.K, g.ldb, BN), mbl = make_map(bl, b_mn, g.N, g.K, g.ldb, BN);
+    dim3 grid(unsigned(g.M / BM), unsigned(g.N / BN));
+    if (BN == 256) {
+      static std::once_flag once;
+      std::call_once(once, [] { cudaFuncSetAttribute(gemm_tf32x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmem); });
+      gemm_tf32x3_kernel<256><<<grid, kThreads, Cfg<256>::kSmem, ctx->stream>>>(mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M),
+                                                                               uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb);
+    } else {
+      static std::once_flag once;
+      std::call_once(once, [] { cudaFuncSetAttribute(gemm_tf32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::kSmem); });
+      gemm_tf32x3_kernel<128><<<grid, kThreads, Cfg<128>::kSmem, ctx->stream>>>(mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M),
+                                                                               uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb);
+    }
   }
   ctx->count_launch();
   cudaError_t err = cudaGetLastError();
