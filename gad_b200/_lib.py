@@ -68,6 +68,8 @@ SIGNATURES = {
     "gadcu_array_to_host": (C.c_int, [P, P]),
     "gadcu_array_alloc": (C.c_int, [P, C.c_int, DP, PP]),
     "gadcu_array_upload": (C.c_int, [P, P, P]),
+    "gadcu_array_upload_async": (C.c_int, [P, P]),
+    "gadcu_ctx_wait_uploads": (C.c_int, [P]),
     "gadcu_array_retain": (C.c_int, [P]),
     "gadcu_array_release": (C.c_int, [P]),
     "gadcu_array_dims": (C.c_int, [P, DP]),

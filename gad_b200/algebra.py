@@ -132,6 +132,10 @@ class Context:
     def synchronize(self) -> None:
         _check(self.lib.gadcu_ctx_synchronize(self.handle))
 
+    def wait_uploads(self) -> None:
+        """The compute stream waits (on the device) for every upload_async issued so far."""
+        _check(self.lib.gadcu_ctx_wait_uploads(self.handle))
+
     def set_fusion(self, fuse: bool) -> None:
         _check(self.lib.gadcu_ctx_set_fusion(self.handle, int(fuse)))
 
@@ -251,6 +255,10 @@ class CuArray:
 
     def upload(self, pinned: np.ndarray, stream: int = 0) -> None:
         _check(self.ctx.lib.gadcu_array_upload(self.handle, pinned.ctypes.data_as(C.c_void_p), C.c_void_p(stream or None)))
+
+    def upload_async(self, pinned: np.ndarray) -> None:
+        """Prefetch from pinned host memory on the copy stream; readers go after ctx.wait_uploads()."""
+        _check(self.ctx.lib.gadcu_array_upload_async(self.handle, pinned.ctypes.data_as(C.c_void_p)))
 
     def device_ptr(self) -> int:
         return int(self.ctx.lib.gadcu_array_device_ptr(self.handle) or 0)

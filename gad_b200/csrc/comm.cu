@@ -103,6 +103,7 @@ gadcu_status gadcu_comm_allreduce_sum(gadcu_comm* comm, gadcu_array* const* arra
     for (size_t i = 0; i < n; i++) {
       gadcu_array* a = arrays[i];
       if (a->lazy() || a->symbolic()) fail(GADCU_ERR_INVALID, "allreduce needs dense arrays");
+      a->buf->mutated();
       nccl_check(nc.AllReduce(a->ptr(), a->ptr(), a->elements(), a->dtype == GADCU_F32 ? ncclFloat32 : ncclFloat64, ncclSum,
                               comm->comm, comm->ctx->stream),
                  "ncclAllReduce");

@@ -103,6 +103,7 @@ struct gadcu_ctx {
   bool fuse = true;
   bool strict_reference = false;  // reproduce the reference's matmul VJP for transposed operands as is
   std::atomic<uint64_t> launches{0};
+  std::atomic<uint64_t> epoch{1};  // bumped by every new tape: scopes the TF32 split cache to one step
   void* pinned_scratch = nullptr;  // 4 KiB pinned staging for scalar reads
   void* dev_scratch = nullptr;     // reduction partials
   size_t dev_scratch_bytes = 0;
@@ -146,6 +147,12 @@ struct Buffer {
   size_t bytes = 0;
   gadcu_ctx* ctx = nullptr;
   std::shared_ptr<Pool> pool;  // null: not owned (external memory)
+  // [hi | lo] TF32 split of this buffer's f32 contents, made by the first tensor-core GEMM that reads it
+  // and reused by the other GEMMs of the same tape (every GEMM operand of the MLP step is read twice:
+  // forward and one backward product). Valid for one tape epoch and until the buffer is written in place.
+  Buffer* split = nullptr;
+  uint64_t split_epoch = 0, split_elems = 0;
+  void mutated();  // call after every in-place write: drops the cached split
   void retain() { refs.fetch_add(1, std::memory_order_relaxed); }
   void release();
 };

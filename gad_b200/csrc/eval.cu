@@ -195,6 +195,7 @@ ArrayRef EvalAlgebra::fused(k::EwOp op, ArrayRef acc, std::initializer_list<cons
   ArrayRef out;
   if (inplace) {
     out = acc;  // update in place: nobody else can observe this buffer
+    out->buf->mutated();
   } else {
     out = new_array(ctx, dt, dims, is_scalar);
   }
@@ -324,7 +325,7 @@ ArrayRef EvalAlgebra::reduce_as(k::RedOp op, const ArrayRef& vin, const Dim4& rd
       const bool inplace = ctx->fuse && acc->unique();
       acc_keep = materialize(acc);
       acc_ptr = acc_keep->ptr();
-      if (inplace) { out = acc; } else { out = new_array(ctx, cur->dtype, nd); }
+      if (inplace) { out = acc; out->buf->mutated(); } else { out = new_array(ctx, cur->dtype, nd); }
     } else {
       out = new_array(ctx, cur->dtype, nd);
     }
@@ -419,11 +420,14 @@ ArrayRef EvalAlgebra::matmul_acc(ArrayRef acc, const ArrayRef& a_in, const Array
   g.strideA = (ad[2] == 1 && ad[3] == 1) ? 0 : ad[0] * ad[1];
   g.strideB = (bd[2] == 1 && bd[3] == 1) ? 0 : bd[0] * bd[1];
   g.strideC = rd[0] * rd[1];
+  if (a->ptr() == a->buf->ptr) g.a_buf = a->buf.get();
+  if (b->ptr() == b->buf->ptr) g.b_buf = b->buf.get();
   ArrayRef out;
   if (acc) {
     if (acc->dims != rd) fail(GADCU_ERR_DIMENSIONS, "Incompatible dimensions for add: " + acc->dims.str() + " " + rd.str());
     if (acc->unique() && ctx->fuse) {
       out = acc;
+      out->buf->mutated();
       g.accumulate = true;
     } else {
       // current + new into a fresh buffer: product first, then one add pass

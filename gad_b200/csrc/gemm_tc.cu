@@ -645,15 +645,31 @@ int pair_variant() {  // GADCU_GEMM_PAIR = off | 32x3 | 16x6 (default 32x3)
 
 }  // namespace
 
+// [hi | lo] of one operand: from the owning buffer's cache when it has a current one, else a fresh split that
+// is left on the buffer for the other GEMMs of this tape. `keep` holds the split alive until the launch is issued.
+static const float* split_operand(gadcu_ctx* ctx, const float* x, uint64_t elems, Buffer* owner, ArrayRef& keep) {
+  const uint64_t epoch = ctx->epoch.load(std::memory_order_relaxed);
+  if (owner && owner->split && owner->split_epoch == epoch && owner->split_elems == elems)
+    return static_cast<const float*>(owner->split->ptr);
+  keep = new_array(ctx, GADCU_F32, Dim4(2 * elems));
+  float* hi = static_cast<float*>(keep->ptr());
+  split(ctx, x, hi, hi + elems, elems);
+  if (owner && !ctx->capturing) {
+    owner->mutated();
+    owner->split = keep->buf.get();
+    owner->split->retain();
+    owner->split_epoch = epoch;
+    owner->split_elems = elems;
+  }
+  return hi;
+}
+
 void launch_gemm_tc(gadcu_ctx* ctx, const GemmArgs& g) {
   const uint64_t a_elems = g.M * g.K, b_elems = g.K * g.N;
-  ArrayRef tmp = new_array(ctx, GADCU_F32, Dim4(2 * (a_elems + b_elems)));
-  float* ah = static_cast<float*>(tmp->ptr());
-  float* al = ah + a_elems;
-  float* bh = al + a_elems;
-  float* bl = bh + b_elems;
-  split(ctx, static_cast<const float*>(g.A), ah, al, a_elems);
-  split(ctx, static_cast<const float*>(g.B), bh, bl, b_elems);
+  ArrayRef keep_a, keep_b;
+  const float* ah = split_operand(ctx, static_cast<const float*>(g.A), a_elems, g.a_buf, keep_a);
+  const float* bh = split_operand(ctx, static_cast<const float*>(g.B), b_elems, g.b_buf, keep_b);
+  const float *al = ah + a_elems, *bl = bh + b_elems;
 
   const bool a_mn = !g.ta;  // stored [M,K] col-major: M contiguous
   const bool b_mn = g.tb;   // stored [N,K] col-major: N contiguous

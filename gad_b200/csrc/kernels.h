@@ -81,6 +81,8 @@ struct GemmArgs {
   uint64_t lda = 0, ldb = 0;  // leading dims of the stored matrices
   uint64_t batch = 1, strideA = 0, strideB = 0, strideC = 0;
   bool accumulate = false;    // C = C + A*B (gradient accumulation fused into the epilogue)
+  Buffer* a_buf = nullptr;    // owning buffers when an operand is a whole dense buffer (TF32 split cache)
+  Buffer* b_buf = nullptr;
 };
 void launch_gemm(gadcu_ctx* ctx, const GemmArgs& g);
 bool gemm_tc_supported(const GemmArgs& g);  // tcgen05 3xTF32 path applies

@@ -58,8 +58,15 @@ void Pool::put(void* p, size_t bytes) {
 
 void Buffer::release() {
   if (refs.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+    if (split) split->release();
     if (pool && ptr) pool->put(ptr, bytes);
     delete this;
+  }
+}
+void Buffer::mutated() {
+  if (split) {
+    split->release();
+    split = nullptr;
   }
 }
 
@@ -216,7 +223,30 @@ gadcu_status gadcu_array_upload(gadcu_array* a, const void* pinned_host, void* s
   return guard([&] {
     if (a->lazy()) fail(GADCU_ERR_INVALID, "upload into a lazy view");
     cudaStream_t s = stream_or_null ? static_cast<cudaStream_t>(stream_or_null) : a->ctx->stream;
+    a->buf->mutated();
     GADCU_CUDA(cudaMemcpyAsync(a->ptr(), pinned_host, a->elements() * a->elem_size(), cudaMemcpyHostToDevice, s));
+  });
+}
+gadcu_status gadcu_array_upload_async(gadcu_array* a, const void* pinned_host) {
+  return guard([&] {
+    if (a->lazy()) fail(GADCU_ERR_INVALID, "upload into a lazy view");
+    gadcu_ctx* ctx = a->ctx;
+    cudaEvent_t ev;
+    GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    GADCU_CUDA(cudaEventRecord(ev, ctx->stream));
+    GADCU_CUDA(cudaStreamWaitEvent(ctx->side_stream, ev, 0));
+    GADCU_CUDA(cudaEventDestroy(ev));
+    a->buf->mutated();
+    GADCU_CUDA(cudaMemcpyAsync(a->ptr(), pinned_host, a->elements() * a->elem_size(), cudaMemcpyHostToDevice, ctx->side_stream));
+  });
+}
+gadcu_status gadcu_ctx_wait_uploads(gadcu_ctx* ctx) {
+  return guard([&] {
+    cudaEvent_t ev;
+    GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    GADCU_CUDA(cudaEventRecord(ev, ctx->side_stream));
+    GADCU_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    GADCU_CUDA(cudaEventDestroy(ev));
   });
 }
 gadcu_status gadcu_array_to_host(const gadcu_array* a, void* host) {
@@ -270,6 +300,7 @@ gadcu_status gadcu_array_add_assign(gadcu_array* self, const gadcu_array* other)
     if (self->dims != other->dims) fail(GADCU_ERR_DIMENSIONS, "add_assign: " + other->dims.str() + " " + self->dims.str());
     if (self->dtype != other->dtype) fail(GADCU_ERR_TYPE, "add_assign: dtype mismatch");
     if (self->lazy()) fail(GADCU_ERR_INVALID, "add_assign into a lazy view");
+    self->buf->mutated();
     k::EwArgs e;
     e.dt = self->dtype; e.nin = 2; e.in[0] = self->ptr(); e.in[1] = other->ptr(); e.bcast[1] = other->bcast1();
     if (other->lazy() && !other->bcast1()) {

@@ -109,6 +109,11 @@ GADCU_API gadcu_status gadcu_array_to_host(const gadcu_array* a, void* host); /*
 GADCU_API gadcu_status gadcu_array_alloc(gadcu_ctx* ctx, gadcu_dtype dt, const gadcu_dim4* dims, gadcu_array** out);
 /* async H2D into an existing, uniquely owned array (static input buffers of a captured step) */
 GADCU_API gadcu_status gadcu_array_upload(gadcu_array* a, const void* pinned_host, void* stream_or_null);
+/* Prefetch: the copy runs on the context's copy stream once everything already issued on the compute stream has
+ * finished (the target may still be read by it), overlapping the launches issued afterwards. Work that reads `a`
+ * must be issued after gadcu_ctx_wait_uploads(), which makes the compute stream wait for the copies (no host sync). */
+GADCU_API gadcu_status gadcu_array_upload_async(gadcu_array* a, const void* pinned_host);
+GADCU_API gadcu_status gadcu_ctx_wait_uploads(gadcu_ctx* ctx);
 GADCU_API gadcu_status gadcu_array_retain(gadcu_array* a);
 GADCU_API gadcu_status gadcu_array_release(gadcu_array* a);
 GADCU_API gadcu_status gadcu_array_dims(const gadcu_array* a, gadcu_dim4* out);
