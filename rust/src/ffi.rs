@@ -1,0 +1,132 @@
+//! `extern "C"` declarations of include/gadcu.h — one entry point per `Eval for af::Array<T>` method of
+//! the reference (gad/src/{core,arith,const_arith,analytic,compare,array,array_compare,matrix}.rs),
+//! plus the native tape / store / sweep entry points (gad/src/graph.rs, store.rs).
+//! SOURCE ONLY (no Rust toolchain in the build image).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+pub type gadcu_status = c_int;
+pub const GADCU_OK: gadcu_status = 0;
+// gad/src/error.rs:9-40
+pub const GADCU_ERR_DIMENSIONS: gadcu_status = 1;
+pub const GADCU_ERR_REDUCED_DIMENSIONS: gadcu_status = 2;
+pub const GADCU_ERR_LENGTHS: gadcu_status = 3;
+pub const GADCU_ERR_EMPTY: gadcu_status = 4;
+pub const GADCU_ERR_MISSING_ID: gadcu_status = 5;
+pub const GADCU_ERR_MISSING_GRADIENT: gadcu_status = 6;
+pub const GADCU_ERR_MISSING_NODE: gadcu_status = 7;
+
+#[repr(C)] pub struct gadcu_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct gadcu_array { _p: [u8; 0] }
+#[repr(C)] pub struct gadcu_algebra { _p: [u8; 0] }
+#[repr(C)] pub struct gadcu_store { _p: [u8; 0] }
+#[repr(C)] pub struct gadcu_comm { _p: [u8; 0] }
+
+#[repr(C)] #[derive(Clone, Copy, PartialEq, Eq, Debug)]
+pub struct gadcu_dim4 { pub d: [u64; 4] }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct gadcu_matprop { pub transposed: u8, pub conjugated: u8 }
+/// gad's `Value<D>` (graph.rs:35-43): data + optional id (`index == 0` is `id: None`).
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct gadcu_value { pub data: *mut gadcu_array, pub arena: u32, pub index: u32 }
+
+pub const GADCU_F32: c_int = 0;
+pub const GADCU_F64: c_int = 1;
+pub const GADCU_EVAL: c_int = 1;
+pub const GADCU_GRAPH1: c_int = 2;
+pub const GADCU_GRAPHN: c_int = 3;
+pub const GADCU_BATCHED1: c_int = 4;
+
+type A = *mut gadcu_algebra;
+type V = *const gadcu_value;
+type O = *mut gadcu_value;
+type D = *const gadcu_dim4;
+
+extern "C" {
+    pub fn gadcu_last_error() -> *const c_char;
+    pub fn gadcu_ctx_create(device: c_int, out: *mut *mut gadcu_ctx) -> gadcu_status;
+    pub fn gadcu_ctx_destroy(ctx: *mut gadcu_ctx) -> gadcu_status;
+    pub fn gadcu_ctx_synchronize(ctx: *mut gadcu_ctx) -> gadcu_status;
+    // arrays: af::Array::new / host / dims / clone / drop
+    pub fn gadcu_array_from_host(ctx: *mut gadcu_ctx, dt: c_int, dims: D, host: *const c_void, out: *mut *mut gadcu_array) -> gadcu_status;
+    pub fn gadcu_array_to_host(a: *const gadcu_array, host: *mut c_void) -> gadcu_status;
+    pub fn gadcu_array_retain(a: *mut gadcu_array) -> gadcu_status;
+    pub fn gadcu_array_release(a: *mut gadcu_array) -> gadcu_status;
+    pub fn gadcu_array_dims(a: *const gadcu_array, out: *mut gadcu_dim4) -> gadcu_status;
+    pub fn gadcu_scalar_from_host(ctx: *mut gadcu_ctx, dt: c_int, v: f64, out: *mut *mut gadcu_array) -> gadcu_status;
+    pub fn gadcu_scalar_to_host(a: *const gadcu_array, out: *mut f64) -> gadcu_status;
+    pub fn gadcu_value_release(v: O) -> gadcu_status;
+    // WeightOps (net.rs:161-180)
+    pub fn gadcu_array_add_assign(this: *mut gadcu_array, other: *const gadcu_array) -> gadcu_status;
+    pub fn gadcu_array_scale(a: *const gadcu_array, lambda: f64, out: *mut *mut gadcu_array) -> gadcu_status;
+    // Check (dims only; the per-family `impl ... for Check` blocks)
+    pub fn gadcu_check_equal(dims: *const D, n: usize, out: *mut gadcu_dim4) -> gadcu_status;
+    pub fn gadcu_check_moddims(v: D, d: D, out: *mut gadcu_dim4) -> gadcu_status;
+    pub fn gadcu_check_tile_as(v: D, r: D, out: *mut gadcu_dim4) -> gadcu_status;
+    pub fn gadcu_check_sum_as(v: D, r: D, out: *mut gadcu_dim4) -> gadcu_status;
+    pub fn gadcu_check_as_scalar(v: D) -> gadcu_status;
+    pub fn gadcu_check_dot(a: D, b: D) -> gadcu_status;
+    pub fn gadcu_check_reduced(v: D, r: D, keeps_shape: c_int, out: *mut gadcu_dim4) -> gadcu_status;
+    pub fn gadcu_check_transpose(v: D, out: *mut gadcu_dim4) -> gadcu_status;
+    pub fn gadcu_check_matmul(a: D, b: D, p1: gadcu_matprop, p2: gadcu_matprop, out: *mut gadcu_dim4) -> gadcu_status;
+    // algebras: Eval::default / Graph1::new / GraphN::new (lib.rs:523-532, graph.rs:77-92), Clone (graph.rs:353-360)
+    pub fn gadcu_algebra_create(ctx: *mut gadcu_ctx, kind: c_int, out: *mut A) -> gadcu_status;
+    pub fn gadcu_algebra_clone(alg: *const gadcu_algebra, out: *mut A) -> gadcu_status;
+    pub fn gadcu_algebra_destroy(alg: A) -> gadcu_status;
+    // CoreAlgebra (core.rs:12-38)
+    pub fn gadcu_variable(g: A, data: *mut gadcu_array, out: O) -> gadcu_status;
+    pub fn gadcu_constant(g: A, data: *mut gadcu_array, out: O) -> gadcu_status;
+    pub fn gadcu_add(g: A, a: V, b: V, out: O) -> gadcu_status;
+    pub fn gadcu_add_all(g: A, vs: *const V, n: usize, out: O) -> gadcu_status;
+    // ArithAlgebra (arith.rs:14-32)
+    pub fn gadcu_sub(g: A, a: V, b: V, out: O) -> gadcu_status;
+    pub fn gadcu_mul(g: A, a: V, b: V, out: O) -> gadcu_status;
+    pub fn gadcu_zeros(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_ones(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_neg(g: A, v: V, out: O) -> gadcu_status;
+    // ConstArithAlgebra (const_arith.rs:14-26); c_is_int = the constant has type i16
+    pub fn gadcu_setc(g: A, v: V, c: f64, c_is_int: c_int, out: O) -> gadcu_status;
+    pub fn gadcu_addc(g: A, v: V, c: f64, c_is_int: c_int, out: O) -> gadcu_status;
+    pub fn gadcu_mulc(g: A, v: V, c: f64, c_is_int: c_int, out: O) -> gadcu_status;
+    pub fn gadcu_powc(g: A, v: V, c: f64, c_is_int: c_int, out: O) -> gadcu_status;
+    // AnalyticAlgebra (analytic.rs:16-56)
+    pub fn gadcu_exp(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_log(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_log1p(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_sin(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_cos(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_tanh(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_sigmoid(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_reciprocal(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_sqrt(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_div(g: A, a: V, b: V, out: O) -> gadcu_status;
+    pub fn gadcu_pow(g: A, v: V, p: V, out: O) -> gadcu_status;
+    // CompareAlgebra (compare.rs:15-66)
+    pub fn gadcu_select_argmax(g: A, v0: V, v1: V, r0_or_null: V, r1_or_null: V, out: O) -> gadcu_status;
+    // ArrayAlgebra (array.rs:13-45)
+    pub fn gadcu_flat(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_moddims(g: A, v: V, dims: D, out: O) -> gadcu_status;
+    pub fn gadcu_tile_as(g: A, v: V, dims: D, out: O) -> gadcu_status;
+    pub fn gadcu_sum_as(g: A, v: V, dims: D, out: O) -> gadcu_status;
+    pub fn gadcu_constant_as(g: A, scalar: V, dims: D, out: O) -> gadcu_status;
+    pub fn gadcu_as_scalar(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_scale(g: A, lambda: V, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_dot(g: A, a: V, b: V, out: O) -> gadcu_status;
+    // MatrixAlgebra (matrix.rs:20-32)
+    pub fn gadcu_matmul(g: A, a: V, b: V, p1: gadcu_matprop, p2: gadcu_matprop, out: O) -> gadcu_status;
+    pub fn gadcu_transpose(g: A, v: V, conjugate: c_int, out: O) -> gadcu_status;
+    // ArrayCompareAlgebra (array_compare.rs:16-22)
+    pub fn gadcu_max_as(g: A, v: V, dims: D, out: O) -> gadcu_status;
+    pub fn gadcu_argmax_as(g: A, v: V, dims: D, out: O) -> gadcu_status;
+    pub fn gadcu_softmax_as(g: A, v: V, dims: D, out: O) -> gadcu_status;
+    // reverse sweep (graph.rs:263-318) and GradientReader::read (store.rs:27-29)
+    pub fn gadcu_evaluate_gradients(g: A, arena: u32, index: u32, seed: *mut gadcu_array, once: c_int, out: *mut *mut gadcu_store) -> gadcu_status;
+    pub fn gadcu_compute_gradients(g: A, arena: u32, index: u32, seed: V, out: *mut *mut gadcu_store) -> gadcu_status;
+    pub fn gadcu_store_get(s: *const gadcu_store, arena: u32, index: u32, out: O, found: *mut c_int) -> gadcu_status;
+    pub fn gadcu_store_destroy(s: *mut gadcu_store) -> gadcu_status;
+    // data parallelism (new)
+    pub fn gadcu_comm_unique_id(out_128_bytes: *mut c_void) -> gadcu_status;
+    pub fn gadcu_comm_init(ctx: *mut gadcu_ctx, nranks: c_int, rank: c_int, id: *const c_void, out: *mut *mut gadcu_comm) -> gadcu_status;
+    pub fn gadcu_comm_allreduce_sum(comm: *mut gadcu_comm, arrays: *const *mut gadcu_array, n: usize) -> gadcu_status;
+    pub fn gadcu_comm_destroy(comm: *mut gadcu_comm) -> gadcu_status;
+}
