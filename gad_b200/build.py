@@ -28,7 +28,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
           "-I", os.path.join(ROOT, "include"), "-I", CSRC, "--expt-relaxed-constexpr", "-Xcudafe", "--diag_suppress=177"]
 NO_FMA = {"ew.cu", "reduce.cu", "batched.cu"}
 SOURCES = ["runtime.cu", "eval.cu", "graph.cu", "capi.cu", "ew.cu", "reduce.cu", "gemm_simt.cu", "gemm_tc.cu",
-           "batched.cu", "comm.cu"]
+           "batched.cu", "comm.cu", "jit.cu"]
 
 
 def _headers_mtime() -> float:

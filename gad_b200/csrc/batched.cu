@@ -14,19 +14,37 @@
 // log1p = ln(1+v) (analytic.rs:203-205), powc with an i16 constant = powi (const_arith.rs:100-103),
 // sigmoid = 1/(1+exp(-v)) (analytic.rs:221-223), select_argmax with None = 0 (compare.rs:168-174).
 // Compiled with -fmad=false: one rounding per tape op, as on the CPU.
+//
+// The same machinery defers the ELEMENTWISE regions of array tapes (north-star subsystem 1): with fusion on,
+// EvalAlgebra::fused records large elementwise ops — forward primitives and the fused VJP bodies alike — into a
+// lane program with one lane per array element instead of launching them (`lazy_elementwise`). A value is computed
+// when something needs its bytes (a reduction, a GEMM, a host read, the end of a reverse sweep for the variables'
+// gradients): ONE kernel evaluates the whole dependency chain of the requested outputs, reading only the arrays
+// at its leaves, so chains of VJPs across nodes cost one pass (C3 at the 4-pass algorithmic traffic),
+// and saved forward values that are themselves cheap elementwise expressions are recomputed instead of re-read —
+// bit-identically: same ops, same order, one rounding each.
+//
+// Programs run through NVRTC-compiled straight-line kernels (jit.cu) — values live in registers — with the
+// interpreter below as the fallback for batched tapes when NVRTC is unavailable.
 #include <cmath>
 #include <algorithm>
 #include <cstring>
+#include <sstream>
+#include <tuple>
 #include <unordered_map>
 
 #include "batched.h"
+#include "jit.h"
 
 namespace gadcu {
 namespace {
 
 enum SymOp : uint16_t {
   S_LOAD, S_LOADU, S_CONST, S_ADD, S_SUB, S_MUL, S_DIV, S_NEG, S_ADDC, S_MULC, S_POWI, S_POWF, S_POW, S_EXP, S_LOG, S_LOG1P,
-  S_SIN, S_COS, S_TANH, S_SIGMOID, S_RECIP, S_SQRT, S_SELECT, S_SELECT_R0, S_SELECT_R1, S_MIN, S_MAX, S_STORE
+  S_SIN, S_COS, S_TANH, S_SIGMOID, S_RECIP, S_SQRT, S_SELECT, S_SELECT_R0, S_SELECT_R1, S_MIN, S_MAX, S_STORE,
+  // array semantics where they differ from the scalar `impl ... for Eval` (ew.cu functors): 0 - v (arith.rs:60-62),
+  // af::log1p, af::minof / af::maxof; tiled loads (a row or a column broadcast over the other dimension)
+  S_NEG0, S_LOG1PF, S_FMIN, S_FMAX, S_LOADCOL, S_LOADROW
 };
 
 struct SymInstr {
@@ -46,28 +64,69 @@ struct SymProgram {
   gadcu_ctx* ctx;
   gadcu_dtype dtype;
   uint64_t lanes;
+  bool array_mode = false;   // lanes are the elements of device arrays (deferred elementwise region of an array tape)
+  uint64_t epoch = 0;        // tape epoch the program was opened in (array mode)
   std::vector<SymInstr> instrs;
-  std::vector<ArrayRef> inputs;                      // real arrays: [lanes] columns or 1-element uniforms
-  std::unordered_map<const void*, int32_t> input_reg;  // dedupe loads by buffer
+  std::vector<ArrayRef> inputs;                      // real arrays: [lanes] columns, 1-element uniforms, row/column tiles
+  std::vector<uint64_t> input_d0;                    // S_LOADCOL / S_LOADROW: dims[0] of the logical array
+  std::map<std::tuple<const void*, int, uint64_t>, int32_t> input_reg;  // dedupe loads by (buffer, kind, d0)
   std::unordered_map<int32_t, ArrayRef> cache;       // register -> materialised column
+  std::vector<int32_t> live;                         // handles alive per register
+  std::map<std::tuple<uint16_t, int32_t, int32_t, int32_t, int32_t, double>, int32_t> value_number;  // array mode: CSE
   uint64_t last_instructions = 0, last_slots = 0;
   std::mutex mu;
 
   int32_t emit(SymInstr i) {
+    if (array_mode && i.op != S_LOAD && i.op != S_LOADU && i.op != S_LOADCOL && i.op != S_LOADROW) {
+      // same op on the same registers gives the same bits: the VJP's recomputed forward (analytic.rs:308,388)
+      // is the forward value itself
+      auto key = std::make_tuple(i.op, i.a, i.b, i.c, i.d, i.imm);
+      auto it = value_number.find(key);
+      if (it != value_number.end()) return it->second;
+      instrs.push_back(i);
+      live.push_back(0);
+      value_number.emplace(key, int32_t(instrs.size() - 1));
+      return int32_t(instrs.size() - 1);
+    }
     instrs.push_back(i);
+    live.push_back(0);
     return int32_t(instrs.size() - 1);
   }
   std::vector<ArrayRef> run(const std::vector<int32_t>& outs);
+  std::vector<ArrayRef> run_interpreter(const std::vector<int32_t>& todo);
+  std::vector<ArrayRef> run_jit(const std::vector<int32_t>& todo);
 };
 
-ArrayRef sym_array(const std::shared_ptr<SymProgram>& prog, int32_t reg) {
+// What a symbolic handle holds: keeps the program alive and counts the handles per register, so that a write
+// into one of the program's input buffers can first force exactly the values somebody can still ask for.
+struct SymRef {
+  std::shared_ptr<SymProgram> prog;
+  int32_t reg;
+  SymRef(std::shared_ptr<SymProgram> p, int32_t r) : prog(std::move(p)), reg(r) {
+    std::lock_guard<std::mutex> lk(prog->mu);
+    prog->live[reg]++;
+  }
+  ~SymRef() {
+    ArrayRef drop;  // released after the lock
+    std::lock_guard<std::mutex> lk(prog->mu);
+    if (--prog->live[reg] == 0 && prog->array_mode) {
+      // nobody can ask for this register any more: its column (if it was computed) goes back to the pool now;
+      // a later value that depends on it recomputes it from its operands
+      auto it = prog->cache.find(reg);
+      if (it != prog->cache.end()) { drop = std::move(it->second); prog->cache.erase(it); }
+    }
+  }
+};
+const std::shared_ptr<SymProgram>& program_of(const gadcu_array* a) { return static_cast<SymRef*>(a->sym.get())->prog; }
+
+ArrayRef sym_array(const std::shared_ptr<SymProgram>& prog, int32_t reg, const Dim4& dims = Dim4(), bool is_scalar = true) {
   auto* a = new gadcu_array;
-  a->dims = Dim4();
-  a->phys = Dim4();
+  a->dims = dims;
+  a->phys = dims;
   a->dtype = prog->dtype;
-  a->is_scalar = true;
+  a->is_scalar = is_scalar;
   a->ctx = prog->ctx;
-  a->sym = prog;
+  a->sym = std::make_shared<SymRef>(prog, reg);
   a->sym_reg = reg;
   return ArrayRef(a, false);
 }
@@ -159,6 +218,9 @@ __global__ void __launch_bounds__(kLaneThreads) lane_interpreter(const DevInstr*
         case S_SELECT_R1: r = s[I.a] >= s[I.b] ? T(0) : s[I.c]; break;
         case S_MIN: r = s[I.a] <= s[I.b] ? s[I.a] : s[I.b]; break;
         case S_MAX: r = s[I.a] >= s[I.b] ? s[I.a] : s[I.b]; break;
+        case S_NEG0: r = T(0) - s[I.a]; break;
+        case S_FMIN: r = fmin(s[I.a], s[I.b]); break;
+        case S_FMAX: r = fmax(s[I.a], s[I.b]); break;
         case S_STORE: out[I.b][lane] = s[I.a]; continue;
         default: continue;
       }
@@ -182,6 +244,14 @@ void launch_interpreter(gadcu_ctx* ctx, int slots, const DevInstr* prog, int n, 
 }
 
 // ---- compile (DCE + liveness slot assignment) and run -------------------------------------------
+bool use_jit() {
+  static const bool interp = [] {
+    const char* e = getenv("GADCU_LANES");
+    return e && std::string(e) == "interp";
+  }();
+  return !interp && jit::available();
+}
+
 std::vector<ArrayRef> SymProgram::run(const std::vector<int32_t>& outs) {
   std::lock_guard<std::mutex> lk(mu);
   std::vector<ArrayRef> result(outs.size());
@@ -194,7 +264,14 @@ std::vector<ArrayRef> SymProgram::run(const std::vector<int32_t>& outs) {
   if (todo.empty()) return result;
   std::sort(todo.begin(), todo.end());
   todo.erase(std::unique(todo.begin(), todo.end()), todo.end());
+  std::vector<ArrayRef> cols = (array_mode || use_jit()) ? run_jit(todo) : run_interpreter(todo);
+  for (size_t j = 0; j < todo.size(); j++) cache[todo[j]] = cols[j];
+  for (size_t i = 0; i < outs.size(); i++)
+    if (!result[i]) result[i] = cache[outs[i]];
+  return result;
+}
 
+std::vector<ArrayRef> SymProgram::run_interpreter(const std::vector<int32_t>& todo) {
   const int32_t n = int32_t(instrs.size());
   // 1. dead-code elimination: what do the requested outputs depend on?
   std::vector<char> needed(n, 0);
@@ -309,10 +386,285 @@ std::vector<ArrayRef> SymProgram::run(const std::vector<int32_t>& outs) {
   if (dtype == GADCU_F32) launch_interpreter<float>(ctx, next_slot, dprog, int(dev.size()), din, dout, lanes);
   else launch_interpreter<double>(ctx, next_slot, dprog, int(dev.size()), din, dout, lanes);
 
-  for (size_t j = 0; j < todo.size(); j++) cache[todo[j]] = out_cols[j];
-  for (size_t i = 0; i < outs.size(); i++)
-    if (!result[i]) result[i] = cache[outs[i]];
-  return result;
+  return out_cols;
+}
+
+// ---- NVRTC path: the program as one straight-line kernel, values in registers ----------------------
+namespace {
+
+const char* op_expr(uint16_t op) {  // %a %b %c %d = operand names, %k = immediate; mirrors the interpreter above / ew.cu
+  switch (op) {
+    case S_CONST: return "%k";
+    case S_ADD: return "%a + %b";
+    case S_SUB: return "%a - %b";
+    case S_MUL: return "%a * %b";
+    case S_DIV: return "%a / %b";
+    case S_NEG: return "-%a";
+    case S_NEG0: return "T(0) - %a";
+    case S_ADDC: return "%a + %k";
+    case S_MULC: return "%a * %k";
+    case S_POWI: return "g_powi(%a, int(%k))";
+    case S_POWF: return "G_POW(%a, %k)";
+    case S_POW: return "G_POW(%a, %b)";
+    case S_EXP: return "G_EXP(%a)";
+    case S_LOG: return "G_LOG(%a)";
+    case S_LOG1P: return "G_LOG(T(1) + %a)";
+    case S_LOG1PF: return "G_LOG1P(%a)";
+    case S_SIN: return "G_SIN(%a)";
+    case S_COS: return "G_COS(%a)";
+    case S_TANH: return "G_TANH(%a)";
+    case S_SIGMOID: return "T(1) / (T(1) + G_EXP(-%a))";
+    case S_RECIP: return "T(1) / %a";
+    case S_SQRT: return "G_SQRT(%a)";
+    case S_SELECT: return "%a >= %b ? %c : %d";
+    case S_SELECT_R0: return "%a >= %b ? %c : T(0)";
+    case S_SELECT_R1: return "%a >= %b ? T(0) : %c";
+    case S_MIN: return "%a <= %b ? %a : %b";
+    case S_MAX: return "%a >= %b ? %a : %b";
+    case S_FMIN: return "G_FMIN(%a, %b)";
+    case S_FMAX: return "G_FMAX(%a, %b)";
+    default: return nullptr;
+  }
+}
+
+struct JitPlan {
+  int V = 1, U = 1, block = 256;
+  bool idx32 = true;
+  std::vector<int32_t> order;                  // needed non-load instructions, ascending
+  std::vector<std::pair<int32_t, int>> dense;  // (register, param slot): dense [lanes] inputs incl. cached values
+  std::vector<std::pair<int32_t, int>> uniform, col, row;
+  std::vector<int32_t> outs;
+  std::vector<double> imms;
+  std::vector<const void*> in_ptrs;
+  std::vector<uint64_t> tile_d0;               // one per col/row input, in (col..., row...) order
+  std::unordered_map<int32_t, int32_t> local;  // program register -> dense numbering of the needed ones, so that the
+                                               // same structure at different positions of a program is the same kernel
+};
+
+const JitPlan* g_plan = nullptr;  // set while a plan is being rendered (single-threaded under the program's mutex)
+std::string reg_name(int32_t r) { return "r" + std::to_string(g_plan->local.at(r)); }
+
+std::string gen_source(const SymProgram& P, const JitPlan& J, const std::unordered_map<int32_t, int>& imm_slot) {
+  const bool f32 = P.dtype == GADCU_F32;
+  std::ostringstream o;
+  o << "typedef " << (f32 ? "float" : "double") << " T;\n";
+  if (J.V == 4) o << "typedef float4 TV;\n";
+  else if (J.V == 2) o << "typedef double2 TV;\n";
+  else o << "typedef T TV;\n";
+  o << "typedef unsigned long long u64;\n";
+  if (f32)
+    o << "#define G_EXP expf\n#define G_LOG logf\n#define G_LOG1P log1pf\n#define G_SIN sinf\n#define G_COS cosf\n#define G_TANH tanhf\n"
+         "#define G_SQRT sqrtf\n#define G_POW powf\n#define G_FMIN fminf\n#define G_FMAX fmaxf\n";
+  else
+    o << "#define G_EXP exp\n#define G_LOG log\n#define G_LOG1P log1p\n#define G_SIN sin\n#define G_COS cos\n#define G_TANH tanh\n"
+         "#define G_SQRT sqrt\n#define G_POW pow\n#define G_FMIN fmin\n#define G_FMAX fmax\n";
+  o << "__device__ __forceinline__ T g_powi(T a, int b) { const bool recip = b < 0; T r = T(1); while (true) { if (b & 1) r *= a; b /= 2; "
+       "if (b == 0) break; a *= a; } return recip ? T(1) / r : r; }\n";
+  const size_t NI = J.in_ptrs.size(), NO = J.outs.size(), NT = J.tile_d0.size(), NM = J.imms.size();
+  o << "struct P { const T* in[" << std::max<size_t>(NI, 1) << "]; T* out[" << std::max<size_t>(NO, 1) << "]; u64 n; u64 td["
+    << std::max<size_t>(NT, 1) << "]; double imm[" << std::max<size_t>(NM, 1) << "]; };\n";
+  // ---- body: one lane
+  o << "__device__ __forceinline__ void body(const P& p, u64 i";
+  for (auto& d : J.dense) o << ", const T " << reg_name(d.first);
+  for (auto& d : J.uniform) o << ", const T " << reg_name(d.first);
+  for (auto& d : J.col) o << ", const T " << reg_name(d.first);
+  for (size_t k = 0; k < NO; k++) o << ", T& o" << k;
+  o << ") {\n";
+  for (size_t k = 0; k < J.row.size(); k++) {
+    const size_t t = J.col.size() + k;
+    o << "  const T " << reg_name(J.row[k].first) << " = p.in[" << J.row[k].second << "]["
+      << (J.idx32 ? "(unsigned)i % (unsigned)p.td[" : "i % p.td[") << t << "]];\n";
+  }
+  for (int32_t r : J.order) {
+    const SymInstr& I = P.instrs[r];
+    const char* e = op_expr(I.op);
+    std::string expr;
+    for (const char* c = e; *c; c++) {
+      if (*c == '%') {
+        c++;
+        switch (*c) {
+          case 'a': expr += reg_name(I.a); break;
+          case 'b': expr += reg_name(I.b); break;
+          case 'c': expr += reg_name(I.c); break;
+          case 'd': expr += reg_name(I.d); break;
+          case 'k': expr += "T(p.imm[" + std::to_string(imm_slot.at(r)) + "])"; break;
+        }
+      } else {
+        expr += *c;
+      }
+    }
+    o << "  const T " << reg_name(r) << " = " << expr << ";\n";
+  }
+  for (size_t k = 0; k < NO; k++) o << "  o" << k << " = " << reg_name(J.outs[k]) << ";\n";
+  o << "}\n";
+  // ---- kernel skeleton: all loads of U vectors first, then compute + store
+  const char* lanes4[] = {".x", ".y", ".z", ".w"};
+  o << "extern \"C\" __global__ void __launch_bounds__(" << J.block << ") lane_program(const P p) {\n";
+  o << "  const u64 tid = (u64)blockIdx.x * " << J.block << "ull + threadIdx.x;\n  const u64 stride = (u64)gridDim.x * " << J.block << "ull;\n";
+  for (auto& d : J.uniform) o << "  const T " << reg_name(d.first) << " = p.in[" << d.second << "][0];\n";
+  auto col_index = [&](size_t k, const std::string& i) {
+    return J.idx32 ? "(unsigned)(" + i + ") / (unsigned)p.td[" + std::to_string(k) + "]" : "(" + i + ") / p.td[" + std::to_string(k) + "]";
+  };
+  if (J.V > 1) {
+    o << "  const u64 nvec = p.n / " << J.V << ";\n";
+    o << "  for (u64 base = tid; base < nvec; base += stride * " << J.U << ") {\n";
+    for (auto& d : J.dense) o << "    TV v" << J.local.at(d.first) << "[" << J.U << "];\n";
+    o << "#pragma unroll\n    for (int u = 0; u < " << J.U << "; u++) {\n      const u64 vi = base + u * stride;\n      if (vi < nvec) {\n";
+    for (auto& d : J.dense) o << "        v" << J.local.at(d.first) << "[u] = __ldcs(reinterpret_cast<const TV*>(p.in[" << d.second << "]) + vi);\n";
+    o << "      }\n    }\n";
+    o << "#pragma unroll\n    for (int u = 0; u < " << J.U << "; u++) {\n      const u64 vi = base + u * stride;\n      if (vi < nvec) {\n";
+    for (size_t k = 0; k < J.col.size(); k++)  // dims[0] is a multiple of V: the V lanes of a vector share the column
+      o << "        const T " << reg_name(J.col[k].first) << " = p.in[" << J.col[k].second << "][" << col_index(k, "vi * " + std::to_string(J.V)) << "];\n";
+    for (size_t k = 0; k < NO; k++) o << "        TV y" << k << ";\n";
+    for (int l = 0; l < J.V; l++) {
+      o << "        body(p, vi * " << J.V << " + " << l;
+      for (auto& d : J.dense) o << ", v" << J.local.at(d.first) << "[u]" << lanes4[l];
+      for (auto& d : J.uniform) o << ", " << reg_name(d.first);
+      for (auto& d : J.col) o << ", " << reg_name(d.first);
+      for (size_t k = 0; k < NO; k++) o << ", y" << k << lanes4[l];
+      o << ");\n";
+    }
+    for (size_t k = 0; k < NO; k++) o << "        reinterpret_cast<TV*>(p.out[" << k << "])[vi] = y" << k << ";\n";
+    o << "      }\n    }\n  }\n";
+    o << "  for (u64 i = nvec * " << J.V << " + tid; i < p.n; i += stride) {\n";
+  } else {
+    o << "  for (u64 i = tid; i < p.n; i += stride) {\n";
+  }
+  // scalar loop (the whole program for V == 1, the tail otherwise)
+  for (auto& d : J.dense) o << "    const T s" << J.local.at(d.first) << " = __ldcs(p.in[" << d.second << "] + i);\n";
+  for (size_t k = 0; k < J.col.size(); k++)
+    o << "    const T " << reg_name(J.col[k].first) << " = p.in[" << J.col[k].second << "][" << col_index(k, "i") << "];\n";
+  for (size_t k = 0; k < NO; k++) o << "    T y" << k << ";\n";
+  o << "    body(p, i";
+  for (auto& d : J.dense) o << ", s" << J.local.at(d.first);
+  for (auto& d : J.uniform) o << ", " << reg_name(d.first);
+  for (auto& d : J.col) o << ", " << reg_name(d.first);
+  for (size_t k = 0; k < NO; k++) o << ", y" << k;
+  o << ");\n";
+  for (size_t k = 0; k < NO; k++) o << "    p.out[" << k << "][i] = y" << k << ";\n";
+  o << "  }\n}\n";
+  return o.str();
+}
+
+}  // namespace
+
+std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
+  const int32_t n = int32_t(instrs.size());
+  auto is_load = [](uint16_t op) { return op == S_LOAD || op == S_LOADU || op == S_LOADCOL || op == S_LOADROW; };
+  // 1. what the requested outputs depend on; a register that already has a materialised column is a leaf
+  std::vector<char> needed(n, 0);
+  std::vector<int32_t> stack(todo.begin(), todo.end());
+  while (!stack.empty()) {
+    int32_t r = stack.back();
+    stack.pop_back();
+    if (needed[r]) continue;
+    needed[r] = 1;
+    const SymInstr& I = instrs[r];
+    if (is_load(I.op) || I.op == S_CONST || cache.count(r)) continue;
+    for (int32_t x : {I.a, I.b, I.c, I.d})
+      if (x >= 0 && !needed[x]) stack.push_back(x);
+  }
+  JitPlan J;
+  J.outs = todo;
+  std::unordered_map<int32_t, int> imm_slot;
+  for (int32_t r = 0; r < n; r++) {
+    if (!needed[r]) continue;
+    J.local.emplace(r, int32_t(J.local.size()));
+    const SymInstr& I = instrs[r];
+    auto cached = cache.find(r);
+    if (cached != cache.end()) {
+      J.dense.push_back({r, int(J.in_ptrs.size())});
+      J.in_ptrs.push_back(cached->second->ptr());
+    } else if (I.op == S_LOAD) {
+      J.dense.push_back({r, int(J.in_ptrs.size())});
+      J.in_ptrs.push_back(inputs[I.a]->ptr());
+    } else if (I.op == S_LOADU) {
+      J.uniform.push_back({r, int(J.in_ptrs.size())});
+      J.in_ptrs.push_back(inputs[I.a]->ptr());
+    } else if (I.op == S_LOADCOL) {
+      J.col.push_back({r, int(J.in_ptrs.size())});
+      J.in_ptrs.push_back(inputs[I.a]->ptr());
+    } else if (I.op == S_LOADROW) {
+      J.row.push_back({r, int(J.in_ptrs.size())});
+      J.in_ptrs.push_back(inputs[I.a]->ptr());
+    } else {
+      J.order.push_back(r);
+      if (I.op == S_CONST || I.op == S_ADDC || I.op == S_MULC || I.op == S_POWI || I.op == S_POWF) {
+        imm_slot[r] = int(J.imms.size());
+        J.imms.push_back(I.imm);
+      }
+    }
+  }
+  for (auto& c : J.col) J.tile_d0.push_back(input_d0[instrs[c.first].a]);
+  for (auto& r : J.row) J.tile_d0.push_back(input_d0[instrs[r.first].a]);
+  // 2. shape of the kernel: 128-bit vectors and several vectors in flight for small programs, one lane per thread
+  //    for long ones (register pressure)
+  const int vmax = dtype == GADCU_F32 ? 4 : 2;
+  J.V = J.order.size() <= 256 ? vmax : 1;
+  for (uint64_t d0 : std::vector<uint64_t>(J.tile_d0.begin(), J.tile_d0.begin() + J.col.size()))
+    if (d0 % uint64_t(J.V) != 0) J.V = 1;
+  const size_t streams = J.dense.size() + J.outs.size();
+  J.U = J.V == 1 ? 1 : (streams <= 4 && J.order.size() <= 64 ? 4 : (streams <= 8 && J.order.size() <= 128 ? 2 : 1));
+  J.block = J.order.size() > 256 ? 128 : 256;
+  J.idx32 = lanes < (1ull << 32);
+  last_instructions = J.order.size() + J.dense.size() + J.uniform.size() + J.col.size() + J.row.size() + J.outs.size();
+  last_slots = J.local.size();  // SSA values of the kernel (they live in registers)
+  // 3. structural key: identical tapes (every training step) reuse the compiled kernel
+  std::string key;
+  key.reserve(J.order.size() * 24 + 64);
+  key += dtype == GADCU_F32 ? "f32" : "f64";
+  key += "|V" + std::to_string(J.V) + "U" + std::to_string(J.U) + "B" + std::to_string(J.block) + (J.idx32 ? "i32" : "i64");
+  auto L = [&](int32_t r) { return r < 0 ? std::string("-") : std::to_string(J.local.at(r)); };
+  auto list = [&](const char* tag, const std::vector<std::pair<int32_t, int>>& v) {
+    key += tag;
+    for (auto& d : v) key += L(d.first) + ",";
+  };
+  list("|d", J.dense);
+  list("|u", J.uniform);
+  list("|c", J.col);
+  list("|r", J.row);
+  key += "|o";
+  for (int32_t r : J.outs) key += L(r) + ",";
+  key += "|";
+  for (int32_t r : J.order) {
+    const SymInstr& I = instrs[r];
+    key += L(r) + ":" + std::to_string(I.op) + "(" + L(I.a) + "," + L(I.b) + "," + L(I.c) + "," + L(I.d) + ");";
+  }
+  const jit::Kernel* kernel = jit::find(key);
+  if (!kernel) {
+    g_plan = &J;
+    const std::string src = gen_source(*this, J, imm_slot);
+    g_plan = nullptr;
+    if (const char* dump = getenv("GADCU_JIT_DUMP")) {
+      FILE* f = fopen(dump, "a");
+      if (f) { fprintf(f, "// ---- key %zu bytes, %zu instructions\n%s\n", key.size(), J.order.size(), src.c_str()); fclose(f); }
+    }
+    kernel = jit::compile(key, src, "lane_program");
+  }
+  // 4. outputs + parameter block (layout of `struct P`: every field is 8 bytes wide)
+  std::vector<ArrayRef> out_cols;
+  for (size_t j = 0; j < todo.size(); j++) out_cols.push_back(new_array(ctx, dtype, Dim4(lanes)));
+  const size_t NI = std::max<size_t>(J.in_ptrs.size(), 1), NO = std::max<size_t>(J.outs.size(), 1), NT = std::max<size_t>(J.tile_d0.size(), 1),
+               NM = std::max<size_t>(J.imms.size(), 1);
+  std::vector<uint64_t> params(NI + NO + 1 + NT + NM, 0);
+  for (size_t i = 0; i < J.in_ptrs.size(); i++) params[i] = reinterpret_cast<uint64_t>(J.in_ptrs[i]);
+  for (size_t i = 0; i < out_cols.size(); i++) params[NI + i] = reinterpret_cast<uint64_t>(out_cols[i]->ptr());
+  params[NI + NO] = lanes;
+  for (size_t i = 0; i < J.tile_d0.size(); i++) params[NI + NO + 1 + i] = J.tile_d0[i];
+  for (size_t i = 0; i < J.imms.size(); i++) std::memcpy(&params[NI + NO + 1 + NT + i], &J.imms[i], 8);
+  if (params.size() * 8 > 4000) fail(GADCU_ERR_UNSUPPORTED, "lane program has too many inputs / outputs / constants for one kernel");
+  const uint64_t per_block = uint64_t(J.block) * uint64_t(J.V) * uint64_t(J.U);
+  uint64_t grid = (lanes + per_block - 1) / per_block;
+  const uint64_t cap = uint64_t(ctx->sm_count) * (J.block == 256 ? 8 : 16);
+  if (grid > cap && J.V > 1) grid = cap;          // grid-stride for the streaming kernels
+  if (grid > 0x7fffffffull) grid = 0x7fffffffull;
+  if (grid == 0) grid = 1;
+  {
+    ProfileScope prof_scope(ctx, array_mode ? PROF_EW : PROF_OTHER);
+    void* args[] = {params.data()};
+    jit::launch(ctx, kernel, unsigned(grid), unsigned(J.block), args);
+  }
+  return out_cols;
 }
 
 // ---- the symbolic per-lane eval algebra ---------------------------------------------------------
@@ -328,8 +680,8 @@ class SymAlgebra final : public Algebra {
   int32_t reg(const Value& v) {
     if (!v.data) fail(GADCU_ERR_INVALID, "batched tape: value has no data");
     const ArrayRef& a = v.data;
-    if (a->sym_reg >= 0) {
-      if (a->sym.get() != prog_.get()) fail(GADCU_ERR_INVALID, "batched tape: value belongs to another tape");
+    if (a->sym_reg >= 0 && a->sym) {
+      if (program_of(a.get()).get() != prog_.get()) fail(GADCU_ERR_INVALID, "batched tape: value belongs to another tape");
       return a->sym_reg;
     }
     if (a->dtype != prog_->dtype) fail(GADCU_ERR_TYPE, "batched tape: dtype mismatch");
@@ -337,13 +689,15 @@ class SymAlgebra final : public Algebra {
     const bool uniform = dense->phys.elements() == 1;
     if (!uniform && dense->elements() != prog_->lanes)
       fail(GADCU_ERR_DIMENSIONS, "batched tape: expected a [lanes] column or a scalar, got " + dense->dims.str());
-    auto it = prog_->input_reg.find(dense->ptr());
+    const auto key = std::make_tuple(static_cast<const void*>(dense->ptr()), uniform ? 1 : 0, uint64_t(0));
+    auto it = prog_->input_reg.find(key);
     if (it != prog_->input_reg.end()) return it->second;
     prog_->inputs.push_back(dense);
+    prog_->input_d0.push_back(0);
     SymInstr I{uint16_t(uniform ? S_LOADU : S_LOAD)};
     I.a = int32_t(prog_->inputs.size() - 1);
     int32_t r = prog_->emit(I);
-    prog_->input_reg[dense->ptr()] = r;
+    prog_->input_reg[key] = r;
     return r;
   }
   Value load(const ArrayRef& a) { return Value(sym_array(prog_, reg(Value(a)))); }
@@ -418,8 +772,203 @@ class SymAlgebra final : public Algebra {
 
 ArrayRef force_symbolic(const ArrayRef& a) {
   if (!a->symbolic()) return a;
-  auto prog = std::static_pointer_cast<SymProgram>(a->sym);
-  return prog->run({a->sym_reg})[0];
+  std::shared_ptr<SymProgram> prog = program_of(a.get());
+  ArrayRef col = prog->run({a->sym_reg})[0];
+  if (!prog->array_mode) return col;
+  // an array value: from now on the handle IS the dense array (same bytes; later uses read it, and the program
+  // loads it instead of recomputing)
+  a->buf = col->buf;  // (the handle keeps its register: later ops of the same region reuse the column)
+  return a;
+}
+
+// =================================================================================================
+// deferred elementwise regions of array tapes
+// =================================================================================================
+namespace {
+
+std::shared_ptr<SymProgram> lazy_program(gadcu_ctx* ctx, gadcu_dtype dt, uint64_t n) {
+  const uint64_t epoch = ctx->epoch.load(std::memory_order_relaxed);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto key = std::make_pair(n, int(dt));
+  auto it = ctx->lazy_programs.find(key);
+  if (it != ctx->lazy_programs.end()) {
+    auto prog = std::static_pointer_cast<SymProgram>(it->second);
+    // a new tape starts a new program (the old one dies with the last handle into it and releases its inputs);
+    // so does a program that has grown long outside any tape
+    if (prog->epoch == epoch && prog->instrs.size() < 8192) return prog;
+  }
+  // drop programs of finished tapes from the table (their handles keep them alive as long as needed)
+  for (auto i = ctx->lazy_programs.begin(); i != ctx->lazy_programs.end();) {
+    if (std::static_pointer_cast<SymProgram>(i->second)->epoch != epoch) i = ctx->lazy_programs.erase(i);
+    else ++i;
+  }
+  auto prog = std::make_shared<SymProgram>();
+  prog->ctx = ctx;
+  prog->dtype = dt;
+  prog->lanes = n;
+  prog->array_mode = true;
+  prog->epoch = epoch;
+  ctx->lazy_programs[key] = prog;
+  return prog;
+}
+
+// register of an operand of an n-element elementwise op
+int32_t lazy_operand(const std::shared_ptr<SymProgram>& prog, const ArrayRef& a_in) {
+  ArrayRef a = a_in;
+  if (a->symbolic()) {
+    if (program_of(a.get()).get() == prog.get()) return a->sym_reg;
+    a = materialize(a);  // a value of an earlier tape / another size class: read its bytes
+  }
+  if (a->sym_reg >= 0 && a->sym && program_of(a.get()).get() == prog.get()) return a->sym_reg;  // forced earlier: the program loads the column
+  int kind = 0;  // 0 dense, 1 uniform, 2 column tile ([1,D] over [B,D]), 3 row tile ([B,1] over [B,D])
+  uint64_t d0 = 0;
+  if (a->bcast1() || (a->elements() == 1 && prog->lanes != 1)) {
+    kind = 1;
+  } else if (a->lazy()) {
+    const Dim4 &d = a->dims, &ph = a->phys;
+    if (ph[0] == 1 && ph[1] == d[1] && d[2] == 1 && d[3] == 1 && ph[2] == 1 && ph[3] == 1) { kind = 2; d0 = d[0]; }
+    else if (ph[0] == d[0] && ph[1] == 1 && ph[2] == 1 && ph[3] == 1) { kind = 3; d0 = d[0]; }
+    else a = materialize(a);
+  }
+  if (kind != 1 && a->elements() != prog->lanes) fail(GADCU_ERR_DIMENSIONS, "elementwise operand of " + a->dims.str() + " in a region of " + std::to_string(prog->lanes) + " elements");
+  const auto key = std::make_tuple(static_cast<const void*>(a->ptr()), kind, d0);
+  auto it = prog->input_reg.find(key);
+  if (it != prog->input_reg.end()) return it->second;
+  prog->inputs.push_back(a);
+  prog->input_d0.push_back(d0);
+  static const SymOp load_op[] = {S_LOAD, S_LOADU, S_LOADCOL, S_LOADROW};
+  SymInstr I{uint16_t(load_op[kind])};
+  I.a = int32_t(prog->inputs.size() - 1);
+  int32_t r = prog->emit(I);
+  prog->input_reg[key] = r;
+  return r;
+}
+
+}  // namespace
+
+bool lazy_enabled(gadcu_ctx* ctx, uint64_t n, bool is_scalar) {
+  return ctx->fuse && ctx->lazy && !is_scalar && n >= ctx->lazy_threshold && jit::available();
+}
+
+// out = [acc +] op(ins...), recorded instead of launched. The instruction sequence of every op is the one its
+// ew.cu functor evaluates (one rounding per step), so the value is bit-identical to the eager kernel's.
+ArrayRef lazy_elementwise(gadcu_ctx* ctx, k::EwOp op, const ArrayRef& acc, const std::vector<const ArrayRef*>& ins, double c, double c2,
+                          gadcu_dtype dt, const Dim4& dims, bool is_scalar) {
+  std::shared_ptr<SymProgram> prog = lazy_program(ctx, dt, dims.elements());
+  int32_t r = -1;
+  {
+  std::lock_guard<std::mutex> lk(prog->mu);
+  int32_t x[4] = {-1, -1, -1, -1};
+  for (size_t i = 0; i < ins.size() && i < 4; i++) x[i] = lazy_operand(prog, *ins[i]);
+  const int32_t racc = acc ? lazy_operand(prog, acc) : -1;
+  auto E = [&](SymOp o, int32_t a = -1, int32_t b = -1, int32_t cc = -1, int32_t d = -1, double imm = 0.0) {
+    SymInstr I{uint16_t(o)};
+    I.a = a; I.b = b; I.c = cc; I.d = d; I.imm = imm;
+    return prog->emit(I);
+  };
+  // the functors take their constants as T(c)
+  const double k = dt == GADCU_F32 ? double(float(c)) : c, k2 = dt == GADCU_F32 ? double(float(c2)) : c2;
+  const int32_t a = x[0], b = x[1], cc = x[2], d = x[3];
+  using O = k::EwOp;
+  switch (op) {
+    case O::ADD: r = E(S_ADD, a, b); break;
+    case O::SUB: r = E(S_SUB, a, b); break;
+    case O::MUL: case O::SCALE: case O::VJP_MUL: r = E(S_MUL, a, b); break;
+    case O::DIV: case O::VJP_LOG: r = E(S_DIV, a, b); break;
+    case O::POW: r = E(S_POW, a, b); break;
+    case O::MIN: r = E(S_FMIN, a, b); break;
+    case O::MAX: r = E(S_FMAX, a, b); break;
+    case O::NEG: case O::VJP_NEG: r = E(S_NEG0, a); break;
+    case O::EXP: r = E(S_EXP, a); break;
+    case O::LOG: r = E(S_LOG, a); break;
+    case O::LOG1P: r = E(S_LOG1PF, a); break;
+    case O::SIN: r = E(S_SIN, a); break;
+    case O::COS: r = E(S_COS, a); break;
+    case O::TANH: r = E(S_TANH, a); break;
+    case O::SIGMOID: r = E(S_SIGMOID, a); break;
+    case O::RECIPROCAL: r = E(S_RECIP, a); break;
+    case O::SQRT: r = E(S_SQRT, a); break;
+    case O::COPY: r = a; break;
+    case O::ADDC: r = E(S_ADDC, a, -1, -1, -1, k); break;
+    case O::MULC: case O::VJP_MULC: r = E(S_MULC, a, -1, -1, -1, k); break;
+    case O::POWC: r = E(S_POWF, a, -1, -1, -1, k); break;
+    case O::SELECT_BOTH: r = E(S_SELECT, a, b, cc, d); break;
+    case O::SELECT_R0: r = E(S_SELECT_R0, a, b, cc); break;
+    case O::SELECT_R1: r = E(S_SELECT_R1, a, b, cc); break;
+    case O::VJP_POWC: { int32_t e = E(S_POWF, b, -1, -1, -1, k2); int32_t f = E(S_MULC, e, -1, -1, -1, k); r = E(S_MUL, f, a); break; }
+    case O::VJP_EXP: { int32_t e = E(S_EXP, b); r = E(S_MUL, a, e); break; }
+    case O::VJP_LOG1P: { int32_t p1 = E(S_ADDC, b, -1, -1, -1, 1.0); r = E(S_DIV, a, p1); break; }
+    case O::VJP_SIN: { int32_t e = E(S_COS, b); r = E(S_MUL, a, e); break; }
+    case O::VJP_COS: { int32_t s = E(S_SIN, b); int32_t e = E(S_NEG0, s); r = E(S_MUL, a, e); break; }
+    case O::VJP_TANH: { int32_t t = E(S_TANH, b); int32_t s = E(S_MUL, t, t); int32_t n = E(S_NEG0, s); int32_t e = E(S_ADDC, n, -1, -1, -1, 1.0); r = E(S_MUL, a, e); break; }
+    case O::VJP_SIGMOID: { int32_t s = E(S_SIGMOID, b); int32_t n = E(S_NEG0, s); int32_t p1 = E(S_ADDC, n, -1, -1, -1, 1.0); int32_t e = E(S_MUL, s, p1); r = E(S_MUL, a, e); break; }
+    case O::VJP_RECIPROCAL: { int32_t s = E(S_MUL, b, b); int32_t n = E(S_NEG0, s); int32_t e = E(S_RECIP, n); r = E(S_MUL, a, e); break; }
+    case O::VJP_SQRT: { int32_t s = E(S_SQRT, b); int32_t s2 = E(S_MULC, s, -1, -1, -1, 2.0); int32_t e = E(S_RECIP, s2); r = E(S_MUL, a, e); break; }
+    case O::VJP_DIV0: { int32_t rr = E(S_RECIP, b); r = E(S_MUL, a, rr); break; }
+    case O::VJP_DIV1: { int32_t rr = E(S_RECIP, b); int32_t g0 = E(S_MUL, a, rr); int32_t e = E(S_MUL, g0, rr); int32_t e2 = E(S_MUL, e, cc); r = E(S_NEG0, e2); break; }
+    case O::VJP_SELECT0: r = E(S_SELECT_R0, b, cc, a); break;
+    case O::VJP_SELECT1: r = E(S_SELECT_R1, b, cc, a); break;
+    default: fail(GADCU_ERR_INVALID, "unknown elementwise op");
+  }
+  if (racc >= 0) r = E(S_ADD, racc, r);  // store.rs:52: current + new
+  }
+  return sym_array(prog, r, dims, is_scalar);
+}
+
+// Before `buffer` is overwritten in place (WeightOps::add_assign, an upload, an all-reduce): compute every value
+// that still has a handle and would read the old contents later.
+void lazy_before_write(gadcu_ctx* ctx, const void* buffer) {
+  std::vector<std::shared_ptr<SymProgram>> progs;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto& kv : ctx->lazy_programs) progs.push_back(std::static_pointer_cast<SymProgram>(kv.second));
+  }
+  for (auto& prog : progs) {
+    std::vector<int32_t> todo;
+    {
+      std::lock_guard<std::mutex> lk(prog->mu);
+      const int32_t n = int32_t(prog->instrs.size());
+      std::vector<char> dep(n, 0);
+      bool any = false;
+      for (int32_t r = 0; r < n; r++) {
+        const SymInstr& I = prog->instrs[r];
+        if (I.op == S_LOAD || I.op == S_LOADU || I.op == S_LOADCOL || I.op == S_LOADROW) {
+          dep[r] = prog->inputs[I.a]->ptr() == buffer;
+        } else if (I.op != S_CONST && !prog->cache.count(r)) {
+          for (int32_t x : {I.a, I.b, I.c, I.d})
+            if (x >= 0 && dep[x]) dep[r] = 1;
+        }
+        any = any || dep[r];
+        if (dep[r] && prog->live[r] > 0 && !prog->cache.count(r) && !(I.op == S_LOAD || I.op == S_LOADU || I.op == S_LOADCOL || I.op == S_LOADROW))
+          todo.push_back(r);
+      }
+      if (!any) continue;
+    }
+    if (!todo.empty()) prog->run(todo);
+  }
+}
+
+// End of a Graph1 sweep: the gradients of the tape's variables are what the caller reads — compute them, all
+// those of one region in one kernel. Other store entries stay deferred until somebody reads them.
+void lazy_flush(const std::vector<ArrayRef>& values) {
+  std::map<SymProgram*, std::pair<std::shared_ptr<SymProgram>, std::vector<size_t>>> groups;
+  for (size_t i = 0; i < values.size(); i++) {
+    const ArrayRef& a = values[i];
+    if (!a || !a->symbolic()) continue;
+    std::shared_ptr<SymProgram> prog = program_of(a.get());
+    if (!prog->array_mode) continue;
+    auto& g = groups[prog.get()];
+    g.first = prog;
+    g.second.push_back(i);
+  }
+  for (auto& kv : groups) {
+    std::vector<int32_t> regs;
+    for (size_t i : kv.second.second) regs.push_back(values[i]->sym_reg);
+    std::vector<ArrayRef> cols = kv.second.first->run(regs);
+    for (size_t j = 0; j < regs.size(); j++) {
+      values[kv.second.second[j]]->buf = cols[j]->buf;
+    }
+  }
 }
 
 std::unique_ptr<GraphAlgebra> make_batched(gadcu_ctx* ctx, gadcu_dtype dt, uint64_t lanes) {

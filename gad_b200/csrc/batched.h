@@ -11,4 +11,12 @@ std::unique_ptr<GraphAlgebra> make_batched(gadcu_ctx* ctx, gadcu_dtype dt, uint6
 // all variables. Other store entries stay symbolic and are computed when read.
 std::unique_ptr<Store> batched_evaluate_gradients(GraphAlgebra& g, Id id, ArrayRef seed, bool once);
 
+
+// ---- deferred elementwise regions of array tapes (batched.cu) ---------------------------------------
+bool lazy_enabled(gadcu_ctx* ctx, uint64_t n, bool is_scalar);
+ArrayRef lazy_elementwise(gadcu_ctx* ctx, k::EwOp op, const ArrayRef& acc, const std::vector<const ArrayRef*>& ins, double c, double c2,
+                          gadcu_dtype dt, const Dim4& dims, bool is_scalar);
+void lazy_before_write(gadcu_ctx* ctx, const void* buffer);
+void lazy_flush(const std::vector<ArrayRef>& values);
+
 }  // namespace gadcu

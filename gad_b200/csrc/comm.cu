@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "algebra.h"
+#include "batched.h"
 
 namespace {
 
@@ -102,7 +103,9 @@ gadcu_status gadcu_comm_allreduce_sum(gadcu_comm* comm, gadcu_array* const* arra
     nccl_check(nc.GroupStart(), "ncclGroupStart");
     for (size_t i = 0; i < n; i++) {
       gadcu_array* a = arrays[i];
+      if (a->symbolic()) materialize(ArrayRef(a, true));  // a deferred elementwise value: compute it (the handle becomes dense)
       if (a->lazy() || a->symbolic()) fail(GADCU_ERR_INVALID, "allreduce needs dense arrays");
+      lazy_before_write(comm->ctx, a->ptr());
       a->buf->mutated();
       nccl_check(nc.AllReduce(a->ptr(), a->ptr(), a->elements(), a->dtype == GADCU_F32 ? ncclFloat32 : ncclFloat64, ncclSum,
                               comm->comm, comm->ctx->stream),

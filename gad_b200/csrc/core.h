@@ -103,7 +103,11 @@ struct gadcu_ctx {
   bool fuse = true;
   bool strict_reference = false;  // reproduce the reference's matmul VJP for transposed operands as is
   std::atomic<uint64_t> launches{0};
-  std::atomic<uint64_t> epoch{1};  // bumped by every new tape: scopes the TF32 split cache to one step
+  std::atomic<uint64_t> epoch{1};
+  // deferred elementwise regions (batched.cu): open lane programs by (element count, dtype)
+  bool lazy = true;
+  uint64_t lazy_threshold = 32768;  // smaller arrays run eagerly (one tiny kernel beats a specialised one)
+  std::map<std::pair<uint64_t, int>, std::shared_ptr<void>> lazy_programs;  // bumped by every new tape: scopes the TF32 split cache to one step
   void* pinned_scratch = nullptr;  // 4 KiB pinned staging for scalar reads
   void* dev_scratch = nullptr;     // reduction partials
   size_t dev_scratch_bytes = 0;

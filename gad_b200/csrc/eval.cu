@@ -3,6 +3,7 @@
 // gad/src/{core,arith,const_arith,analytic,compare,array,array_compare,matrix}.rs: every fallible op
 // runs the Check rule on the host first and launches only if it passes.
 #include "algebra.h"
+#include "batched.h"
 
 namespace gadcu {
 
@@ -131,7 +132,7 @@ struct Operand {
   bool bcast;
 };
 Operand operand(const ArrayRef& a) {
-  if (a->symbolic()) fail(GADCU_ERR_UNSUPPORTED, "a batched-tape lane value cannot be used by an array algebra");
+  if (a->symbolic()) { ArrayRef m = materialize(a); return {m, m->ptr(), false}; }  // a deferred elementwise value: compute it
   if (a->bcast1()) return {a, a->ptr(), true};
   if (a->lazy()) { ArrayRef m = materialize(a); return {m, m->ptr(), false}; }
   return {a, a->ptr(), false};
@@ -158,6 +159,18 @@ ArrayRef EvalAlgebra::fused(k::EwOp op, ArrayRef acc, std::initializer_list<cons
     if ((*p)->dims != dims) {  // a broadcast operand adopts the dims of the dense ones
       if (first->bcast1() || first->elements() == 1) { dims = (*p)->dims; is_scalar = (*p)->is_scalar; }
     }
+  }
+  if (acc) {
+    if (acc->dtype != dt) fail(GADCU_ERR_TYPE, "fused: accumulator dtype mismatch");
+    if (acc->dims != dims) fail(GADCU_ERR_DIMENSIONS, "Incompatible dimensions for add: " + acc->dims.str() + " " + dims.str());
+  }
+  {
+    // large elementwise work is recorded into the tape's lane program instead of launched (batched.cu): the
+    // chain it belongs to becomes one kernel when its bytes are needed
+    bool every_bcast = !acc || acc->bcast1();
+    for (auto p : ins) every_bcast = every_bcast && (*p)->bcast1();
+    if (!every_bcast && lazy_enabled(ctx, dims.elements(), is_scalar))
+      return lazy_elementwise(ctx, op, acc, std::vector<const ArrayRef*>(ins), c, c2, dt, dims, is_scalar);
   }
   // decided before any further handle copies are made: is `acc` ours alone?
   const bool inplace = acc && ctx->fuse && acc->unique();
@@ -284,6 +297,14 @@ Value EvalAlgebra::tile_as(const Value& v, const Dim4& rd) {  // array.rs:76-84
   if (v.data->dims == rd) return Value(v.data);
   if (v.data->phys.elements() == 1) return Value(view_array(v.data, rd, Dim4(), false));  // lazy scalar broadcast
   ArrayRef src = materialize(v.data);
+  if (lazy_enabled(ctx, rd.elements(), false)) {
+    // a row or a column repeated over the other dimension (the bias of a layer): stays a view; the elementwise
+    // kernel that consumes it indexes the small array
+    const Dim4& sd = src->dims;
+    const bool col = sd[0] == 1 && sd[1] == rd[1] && sd[2] == 1 && sd[3] == 1 && rd[2] == 1 && rd[3] == 1;
+    const bool row = sd[0] == rd[0] && sd[1] == 1 && sd[2] == 1 && sd[3] == 1;
+    if (col || row) return Value(view_array(src, rd, sd, false));
+  }
   ArrayRef out = new_array(ctx, src->dtype, rd);
   k::launch_tile(ctx, src->dtype, src->ptr(), src->dims, out->ptr(), rd);
   return Value(out);

@@ -9,6 +9,7 @@
 //     element and folds in `current + new` of add_gradient, in place when the store owns the
 //     buffer alone — no intermediate array ever reaches HBM.
 #include "algebra.h"
+#include "batched.h"
 
 using namespace gadcu;
 
@@ -661,7 +662,22 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
 // graph.rs:263-290: the gradient algebra is a clone of the eval algebra; gradients are pure data.
 std::unique_ptr<Store> GraphAlgebra::evaluate_gradients(Id id, ArrayRef seed, bool once) {
   if (higher_order_) fail(GADCU_ERR_INVALID, "evaluate_gradients is defined for Graph1; use compute_gradients on GraphN");
-  return sweep(*eval_, id, Value(std::move(seed)), once);
+  // the variables' gradients are what the caller came for: their deferred elementwise chains are computed when the
+  // sweep ends, all of one region in one kernel (asked before a consuming sweep clears the nodes)
+  std::vector<Id> var_ids;
+  if (ctx->lazy && ctx->fuse && eval_->is_eval())
+    for (uint32_t i = 1; i <= nodes_.size(); i++)
+      if (is_variable(Id{arena_id_, i})) var_ids.push_back(Id{arena_id_, i});
+  std::unique_ptr<Store> store = sweep(*eval_, id, Value(std::move(seed)), once);
+  if (!var_ids.empty()) {
+    std::vector<ArrayRef> grads;
+    for (Id v : var_ids) {
+      auto it = store->values.find(v);
+      if (it != store->values.end() && it->second.data) grads.push_back(it->second.data);
+    }
+    lazy_flush(grads);
+  }
+  return store;
 }
 
 // graph.rs:307-318: walk (and consume) a clone while `self` records the VJP operations.

@@ -2,6 +2,7 @@
 #include <cstring>
 
 #include "algebra.h"
+#include "batched.h"
 #include "kernels.h"
 
 namespace gadcu {
@@ -87,7 +88,8 @@ ArrayRef new_array(gadcu_ctx* ctx, gadcu_dtype dt, const Dim4& dims, bool is_sca
   return ArrayRef(a, false);
 }
 
-ArrayRef view_array(const ArrayRef& src, const Dim4& dims, const Dim4& phys, bool is_scalar) {
+ArrayRef view_array(const ArrayRef& src_in, const Dim4& dims, const Dim4& phys, bool is_scalar) {
+  ArrayRef src = src_in->symbolic() ? materialize(src_in) : src_in;  // a view needs bytes to point at
   auto* a = new gadcu_array;
   a->buf = src->buf;
   a->dims = dims;
@@ -223,6 +225,7 @@ gadcu_status gadcu_array_upload(gadcu_array* a, const void* pinned_host, void* s
   return guard([&] {
     if (a->lazy()) fail(GADCU_ERR_INVALID, "upload into a lazy view");
     cudaStream_t s = stream_or_null ? static_cast<cudaStream_t>(stream_or_null) : a->ctx->stream;
+    lazy_before_write(a->ctx, a->ptr());
     a->buf->mutated();
     GADCU_CUDA(cudaMemcpyAsync(a->ptr(), pinned_host, a->elements() * a->elem_size(), cudaMemcpyHostToDevice, s));
   });
@@ -231,6 +234,7 @@ gadcu_status gadcu_array_upload_async(gadcu_array* a, const void* pinned_host) {
   return guard([&] {
     if (a->lazy()) fail(GADCU_ERR_INVALID, "upload into a lazy view");
     gadcu_ctx* ctx = a->ctx;
+    lazy_before_write(ctx, a->ptr());
     cudaEvent_t ev;
     GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     GADCU_CUDA(cudaEventRecord(ev, ctx->stream));
@@ -262,6 +266,9 @@ gadcu_status gadcu_array_dims(const gadcu_array* a, gadcu_dim4* out) { *out = a-
 gadcu_dtype gadcu_array_dtype(const gadcu_array* a) { return a->dtype; }
 int gadcu_array_is_scalar(const gadcu_array* a) { return a->is_scalar ? 1 : 0; }
 void* gadcu_array_device_ptr(const gadcu_array* a) {
+  if (a->symbolic() && !a->is_scalar) {  // a deferred elementwise array value: compute it, the handle becomes dense
+    if (guard([&] { materialize(ArrayRef(const_cast<gadcu_array*>(a), true)); }) != GADCU_OK) return nullptr;
+  }
   if (a->lazy() || a->symbolic()) return nullptr;
   return a->ptr();
 }
@@ -300,6 +307,10 @@ gadcu_status gadcu_array_add_assign(gadcu_array* self, const gadcu_array* other)
     if (self->dims != other->dims) fail(GADCU_ERR_DIMENSIONS, "add_assign: " + other->dims.str() + " " + self->dims.str());
     if (self->dtype != other->dtype) fail(GADCU_ERR_TYPE, "add_assign: dtype mismatch");
     if (self->lazy()) fail(GADCU_ERR_INVALID, "add_assign into a lazy view");
+    if (self->symbolic()) materialize(ArrayRef(self, true));
+    ArrayRef other_dense = other->symbolic() ? materialize(ArrayRef(const_cast<gadcu_array*>(other), true)) : ArrayRef(const_cast<gadcu_array*>(other), true);
+    other = other_dense.get();
+    lazy_before_write(self->ctx, self->ptr());
     self->buf->mutated();
     k::EwArgs e;
     e.dt = self->dtype; e.nin = 2; e.in[0] = self->ptr(); e.in[1] = other->ptr(); e.bcast[1] = other->bcast1();
