@@ -67,6 +67,7 @@ SIGNATURES = {
     "gadcu_array_from_host": (C.c_int, [P, C.c_int, DP, P, PP]),
     "gadcu_array_to_host": (C.c_int, [P, P]),
     "gadcu_array_alloc": (C.c_int, [P, C.c_int, DP, PP]),
+    "gadcu_ctx_set_lazy": (C.c_int, [P, C.c_int, C.c_uint64]),
     "gadcu_array_upload": (C.c_int, [P, P, P]),
     "gadcu_array_upload_async": (C.c_int, [P, P]),
     "gadcu_ctx_wait_uploads": (C.c_int, [P]),

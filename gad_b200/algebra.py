@@ -139,6 +139,10 @@ class Context:
     def set_fusion(self, fuse: bool) -> None:
         _check(self.lib.gadcu_ctx_set_fusion(self.handle, int(fuse)))
 
+    def set_lazy(self, enable: bool = True, min_elements: int = 32768) -> None:
+        """Deferred elementwise regions (gadcu_ctx_set_lazy): on by default for arrays of >= 32768 elements."""
+        _check(self.lib.gadcu_ctx_set_lazy(self.handle, int(enable), int(min_elements)))
+
     def set_strict_reference(self, strict: bool) -> None:
         """True: reproduce the reference's matmul VJP for transposed operands as is."""
         _check(self.lib.gadcu_ctx_set_strict_reference(self.handle, int(strict)))

@@ -169,6 +169,11 @@ gadcu_status gadcu_ctx_set_fusion(gadcu_ctx* ctx, int fuse) {
   ctx->fuse = fuse != 0;
   return GADCU_OK;
 }
+gadcu_status gadcu_ctx_set_lazy(gadcu_ctx* ctx, int enable, uint64_t min_elements) {
+  ctx->lazy = enable != 0;
+  ctx->lazy_threshold = min_elements < 2 ? 2 : min_elements;  // single elements (gad's scalars) always run eagerly
+  return GADCU_OK;
+}
 gadcu_status gadcu_ctx_set_strict_reference(gadcu_ctx* ctx, int strict) {
   ctx->strict_reference = strict != 0;
   return GADCU_OK;

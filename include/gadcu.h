@@ -93,6 +93,11 @@ GADCU_API gadcu_status gadcu_ctx_set_fusion(gadcu_ctx* ctx, int fuse);
  * correct adjoint in those cases, which GraphN needs to differentiate through recorded backward
  * GEMMs (Hessian-vector products). Identical wherever the reference formula is valid. */
 GADCU_API gadcu_status gadcu_ctx_set_strict_reference(gadcu_ctx* ctx, int strict);
+/* Deferred elementwise regions (on by default when fusion is on and NVRTC loads): elementwise ops on arrays of at
+ * least `min_elements` elements are recorded and run as ONE specialised kernel per dependency chain when their
+ * bytes are needed (a reduction, a GEMM, a host read, the end of a reverse sweep). Values are bit-identical to
+ * the eager kernels'. enable = 0 restores one kernel per op / per VJP contribution. */
+GADCU_API gadcu_status gadcu_ctx_set_lazy(gadcu_ctx* ctx, int enable, uint64_t min_elements);
 GADCU_API gadcu_status gadcu_ctx_memory_stats(gadcu_ctx* ctx, uint64_t* bytes_in_use, uint64_t* bytes_reserved,
                                               uint64_t* kernel_launches);
 
