@@ -439,6 +439,11 @@ struct JitPlan {
   std::vector<uint64_t> tile_d0;               // one per col/row input, in (col..., row...) order
   std::unordered_map<int32_t, int32_t> local;  // program register -> dense numbering of the needed ones, so that the
                                                // same structure at different positions of a program is the same kernel
+  // long programs (a whole scalar tape, forward + reverse): one lane per thread, and the instructions — loads and
+  // stores included — re-ordered to keep few values alive at a time, so the kernel fits the register file with
+  // enough resident warps to stream from HBM. Any order that respects the data flow gives the same bits.
+  bool flat = false;
+  std::vector<int32_t> sched;
 };
 
 const JitPlan* g_plan = nullptr;  // set while a plan is being rendered (single-threaded under the program's mutex)
@@ -463,6 +468,55 @@ std::string gen_source(const SymProgram& P, const JitPlan& J, const std::unorder
   const size_t NI = J.in_ptrs.size(), NO = J.outs.size(), NT = J.tile_d0.size(), NM = J.imms.size();
   o << "struct P { const T* in[" << std::max<size_t>(NI, 1) << "]; T* out[" << std::max<size_t>(NO, 1) << "]; u64 n; u64 td["
     << std::max<size_t>(NT, 1) << "]; double imm[" << std::max<size_t>(NM, 1) << "]; };\n";
+  if (J.flat) {
+    std::unordered_map<int32_t, int> in_slot, out_slot, tile_slot;
+    for (auto& d : J.dense) in_slot[d.first] = d.second;
+    for (auto& d : J.uniform) in_slot[d.first] = d.second;
+    for (size_t k = 0; k < J.col.size(); k++) { in_slot[J.col[k].first] = J.col[k].second; tile_slot[J.col[k].first] = int(k); }
+    for (size_t k = 0; k < J.row.size(); k++) { in_slot[J.row[k].first] = J.row[k].second; tile_slot[J.row[k].first] = int(J.col.size() + k); }
+    for (size_t k = 0; k < NO; k++) out_slot[J.outs[k]] = int(k);
+    static const int min_blocks = [] { const char* e = getenv("GADCU_LANE_MINBLOCKS"); return e ? atoi(e) : 6; }();  // 6 x 128 threads: <= 80 registers, 24 warps per SM (measured best on C2)
+    o << "extern \"C\" __global__ void __launch_bounds__(" << J.block;
+    if (min_blocks > 0) o << ", " << min_blocks;
+    o << ") lane_program(const P p) {\n";
+    o << "  const u64 tid = (u64)blockIdx.x * " << J.block << "ull + threadIdx.x;\n  const u64 stride = (u64)gridDim.x * " << J.block << "ull;\n";
+    o << "  for (u64 i = tid; i < p.n; i += stride) {\n";
+    for (int32_t r : J.sched) {
+      const SymInstr& I = P.instrs[r];
+      const bool cached = P.cache.count(r) != 0;
+      if (cached || I.op == S_LOAD) {
+        o << "    const T " << reg_name(r) << " = __ldcs(p.in[" << in_slot.at(r) << "] + i);\n";
+      } else if (I.op == S_LOADU) {
+        o << "    const T " << reg_name(r) << " = p.in[" << in_slot.at(r) << "][0];\n";
+      } else if (I.op == S_LOADCOL) {
+        o << "    const T " << reg_name(r) << " = p.in[" << in_slot.at(r) << "][" << (J.idx32 ? "(unsigned)i / (unsigned)p.td[" : "i / p.td[") << tile_slot.at(r) << "]];\n";
+      } else if (I.op == S_LOADROW) {
+        o << "    const T " << reg_name(r) << " = p.in[" << in_slot.at(r) << "][" << (J.idx32 ? "(unsigned)i % (unsigned)p.td[" : "i % p.td[") << tile_slot.at(r) << "]];\n";
+      } else {
+        const char* e = op_expr(I.op);
+        std::string expr;
+        for (const char* c = e; *c; c++) {
+          if (*c == '%') {
+            c++;
+            switch (*c) {
+              case 'a': expr += reg_name(I.a); break;
+              case 'b': expr += reg_name(I.b); break;
+              case 'c': expr += reg_name(I.c); break;
+              case 'd': expr += reg_name(I.d); break;
+              case 'k': expr += "T(p.imm[" + std::to_string(imm_slot.at(r)) + "])"; break;
+            }
+          } else {
+            expr += *c;
+          }
+        }
+        o << "    const T " << reg_name(r) << " = " << expr << ";\n";
+      }
+      auto os = out_slot.find(r);
+      if (os != out_slot.end()) o << "    p.out[" << os->second << "][i] = " << reg_name(r) << ";\n";
+    }
+    o << "  }\n}\n";
+    return o.str();
+  }
   // ---- body: one lane
   o << "__device__ __forceinline__ void body(const P& p, u64 i";
   for (auto& d : J.dense) o << ", const T " << reg_name(d.first);
@@ -607,13 +661,131 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   J.U = J.V == 1 ? 1 : (streams <= 4 && J.order.size() <= 64 ? 4 : (streams <= 8 && J.order.size() <= 128 ? 2 : 1));
   J.block = J.order.size() > 256 ? 128 : 256;
   J.idx32 = lanes < (1ull << 32);
+  if (J.V == 1 && J.order.size() > 256) {
+    // greedy list scheduling for few live values: among the ready instructions take the one that ends the most
+    // live ranges (net of the one it starts); prefer computing over loading, then tape order
+    J.flat = true;
+    std::vector<int32_t> nodes;  // needed registers, ascending
+    for (int32_t r = 0; r < n; r++)
+      if (needed[r]) nodes.push_back(r);
+    auto operands_of = [&](int32_t r, int32_t (&ops)[4]) {
+      const SymInstr& I = instrs[r];
+      if (is_load(I.op) || I.op == S_CONST || cache.count(r)) return 0;
+      int k = 0;
+      for (int32_t x : {I.a, I.b, I.c, I.d})
+        if (x >= 0) {
+          bool dup = false;
+          for (int j = 0; j < k; j++) dup = dup || ops[j] == x;
+          if (!dup) ops[k++] = x;
+        }
+      return k;
+    };
+    std::unordered_map<int32_t, int> uses, pending;        // remaining consumers; unscheduled operands
+    std::unordered_map<int32_t, std::vector<int32_t>> consumers;
+    for (int32_t r : nodes) {
+      int32_t ops[4];
+      const int k = operands_of(r, ops);
+      pending[r] = k;
+      for (int j = 0; j < k; j++) { uses[ops[j]]++; consumers[ops[j]].push_back(r); }
+    }
+    std::vector<int32_t> ready;
+    for (int32_t r : nodes)
+      if (pending[r] == 0) ready.push_back(r);
+    J.sched.reserve(nodes.size());
+    std::unordered_map<int32_t, int> when;  // position in the schedule
+    auto place = [&](int32_t r) {
+      when[r] = int(J.sched.size());
+      J.sched.push_back(r);
+      int32_t ops[4];
+      const int k = operands_of(r, ops);
+      for (int j = 0; j < k; j++) uses[ops[j]]--;
+      for (int32_t cns : consumers[r])
+        if (--pending[cns] == 0) ready.push_back(cns);
+    };
+    {  // lane-invariant values (the seed, constants) first: they are alive throughout anyway, and the reverse
+       // instructions that need them become ready as soon as their forward values exist
+      std::vector<int32_t> invariant;
+      for (size_t c = 0; c < ready.size();) {
+        const SymInstr& I = instrs[ready[c]];
+        if ((I.op == S_LOADU || I.op == S_CONST) && !cache.count(ready[c])) {
+          invariant.push_back(ready[c]);
+          ready[c] = ready.back();
+          ready.pop_back();
+        } else {
+          c++;
+        }
+      }
+      std::sort(invariant.begin(), invariant.end());
+      for (int32_t r : invariant) place(r);
+    }
+    while (!ready.empty()) {
+      // key, larger is better: (live ranges ended - started, computes rather than loads, continues from the most
+      // recently produced value [depth first: finish a chain before opening another], a load that completes a waiting
+      // instruction, tape order)
+      size_t best = 0;
+      std::tuple<int, int, int, int, int32_t> best_key{-1000, 0, 0, 0, 0};
+      for (size_t c = 0; c < ready.size(); c++) {
+        const int32_t r = ready[c];
+        int32_t ops[4];
+        const int k = operands_of(r, ops);
+        int freed = 0, recent = -1;
+        for (int j = 0; j < k; j++) {
+          if (uses[ops[j]] == 1) freed++;
+          recent = std::max(recent, when[ops[j]]);
+        }
+        int completes = 0;
+        if (k == 0)
+          for (int32_t cns : consumers[r]) completes = std::max(completes, pending[cns] == 1 ? 1 : 0);
+        const std::tuple<int, int, int, int, int32_t> key{freed - (uses[r] > 0 ? 1 : 0), k == 0 ? 0 : 1, recent, completes, -r};
+        if (c == 0 || key > best_key) {
+          best = c;
+          best_key = key;
+        }
+      }
+      const int32_t r = ready[best];
+      ready[best] = ready.back();
+      ready.pop_back();
+      place(r);
+    }
+    {  // software pipelining of the lane loads: the load that was about to be used is replaced, in place, by the load
+       // needed kPrefetch loads later, and the first kPrefetch are issued up front — every warp keeps kPrefetch
+       // independent 256-byte requests in flight (one in flight per warp cannot cover HBM latency at any occupancy)
+      static const size_t kPrefetch = [] { const char* e = getenv("GADCU_LANE_PREFETCH"); return e ? size_t(atoi(e)) : size_t(8); }();
+      std::vector<int32_t> lane_loads;
+      for (int32_t r : J.sched)
+        if (cache.count(r) || instrs[r].op == S_LOAD || instrs[r].op == S_LOADCOL || instrs[r].op == S_LOADROW) lane_loads.push_back(r);
+      if (lane_loads.size() > kPrefetch) {
+        std::unordered_map<int32_t, size_t> load_index;
+        for (size_t j = 0; j < lane_loads.size(); j++) load_index[lane_loads[j]] = j;
+        std::vector<int32_t> out;
+        out.reserve(J.sched.size());
+        bool primed = false;
+        for (int32_t r : J.sched) {
+          auto it = load_index.find(r);
+          if (it == load_index.end()) {
+            out.push_back(r);
+            continue;
+          }
+          if (!primed) {
+            for (size_t j = 0; j < kPrefetch; j++) out.push_back(lane_loads[j]);
+            primed = true;
+          }
+          if (it->second + kPrefetch < lane_loads.size()) out.push_back(lane_loads[it->second + kPrefetch]);
+        }
+        J.sched.swap(out);
+      }
+    }
+    // register names follow the schedule, so equal structures still give equal source text
+    J.local.clear();
+    for (int32_t r : J.sched) J.local.emplace(r, int32_t(J.local.size()));
+  }
   last_instructions = J.order.size() + J.dense.size() + J.uniform.size() + J.col.size() + J.row.size() + J.outs.size();
   last_slots = J.local.size();  // SSA values of the kernel (they live in registers)
   // 3. structural key: identical tapes (every training step) reuse the compiled kernel
   std::string key;
   key.reserve(J.order.size() * 24 + 64);
   key += dtype == GADCU_F32 ? "f32" : "f64";
-  key += "|V" + std::to_string(J.V) + "U" + std::to_string(J.U) + "B" + std::to_string(J.block) + (J.idx32 ? "i32" : "i64");
+  key += "|V" + std::to_string(J.V) + "U" + std::to_string(J.U) + "B" + std::to_string(J.block) + (J.idx32 ? "i32" : "i64") + (J.flat ? "flat" : "");
   auto L = [&](int32_t r) { return r < 0 ? std::string("-") : std::to_string(J.local.at(r)); };
   auto list = [&](const char* tag, const std::vector<std::pair<int32_t, int>>& v) {
     key += tag;

@@ -11,6 +11,8 @@
 
 #include <dlfcn.h>
 
+#include <cstdio>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -105,6 +107,15 @@ const Kernel* compile(const std::string& key, const std::string& source, const c
   Kernel k;
   GADCU_CUDA(cudaLibraryLoadData(&k.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   GADCU_CUDA(cudaLibraryGetKernel(&k.fn, k.lib, entry));
+  if (const char* dump = getenv("GADCU_JIT_DUMP")) {
+    cudaFuncAttributes attr;
+    if (cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(k.fn)) == cudaSuccess) {
+      if (FILE* f = fopen(dump, "a")) {
+        fprintf(f, "// compiled: %d registers, %zu bytes local (spills), %zu bytes cubin\n", attr.numRegs, attr.localSizeBytes, cubin.size());
+        fclose(f);
+      }
+    }
+  }
   Cache& c = cache();
   std::lock_guard<std::mutex> lk(c.mu);
   auto res = c.kernels.emplace(key, k);
