@@ -182,6 +182,8 @@ def run_ours(args):
     import gad_b200 as gb
     from gad_b200 import workloads as wl
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -215,12 +217,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
+        t_host = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_ms[0] = (time.perf_counter() - t_host) * 1e3 / steps  # time to ISSUE a step (the device may lag behind)
         e1.record(ext)
         e1.synchronize()
         ms = e0.elapsed_time(e1)
@@ -233,8 +239,10 @@ def run_ours(args):
 
     keep = {}
 
+    overlap = os.environ.get("GADCU_DP_OVERLAP", "0") == "1"  # measured slower on 2x B200: DESIGN.md §8
+
     def step_resident():
-        keep["out"] = wl.mlp_step(ctx, X, Ws, bs, T, comm)
+        keep["out"] = wl.mlp_step(ctx, X, Ws, bs, T, comm, overlap)
 
     for _ in range(max(3, args.warmup)):
         step_resident()
@@ -246,6 +254,7 @@ def run_ours(args):
     ms = timed(step_resident, args.steps)
     prof = ctx.profile_end()
     launches = ctx.launches() - launches0
+    host_issue_ms = host_ms[0]
     clocks = sampler.summary() if rank == 0 else None
     loss_val = keep["out"][0].item()
     steps_per_s = args.steps / (ms / 1000.0)
@@ -272,7 +281,7 @@ def run_ours(args):
         ctx.wait_uploads()       # this step's inputs (copied during the previous step)
         prefetch(i + 1)          # next step's inputs, overlapping this step's kernels
         bx, bt = bufs[i % 2]
-        out = wl.mlp_step(ctx, bx, Ws, bs, bt, comm)
+        out = wl.mlp_step(ctx, bx, Ws, bs, bt, comm, overlap)
         e2e_loss["v"] = out[0].item()  # device -> host read of the step's result
         e2e_i[0] = i + 1
 
@@ -313,10 +322,11 @@ def run_ours(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C4 3-layer tanh MLP {D}-wide, batch {B_TOTAL}, f32, Graph1 fwd + reverse sweep", "global_batch": B_TOTAL,
-                       "rows_per_gpu": rows, "parallelism": f"dp{world} (batch rows sharded, NCCL allreduce of weight grads)",
+                       "rows_per_gpu": rows, "parallelism": f"dp{world} (batch rows sharded, NCCL allreduce of weight grads" + (", overlapped with the sweep)" if overlap and world > 1 else ")"),
                        "l2": "inputs larger than L2 (activations 128 MiB, weights 64 MiB each vs 126 MB L2)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "kernel_time_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}, "loss": loss_val}
+            "kernel_time_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}, "host_issue_ms_per_step": host_issue_ms,
+            "loss": loss_val}
 
     if world == 1 and not args.headline_only:
         try:
@@ -410,6 +420,32 @@ def secondary_metrics(ctx, ext, torch, gb, wl, pk, args):
         "program_instructions": stats["instructions"], "program_slots": stats["slots"],
         "roofline": {"bound": "hbm", "achieved": gps * alg / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": gps * alg / 1e9 / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_gradient": alg}}
+    del cols, res
+
+    # ---- C5: Hessian-vector product of the MLP loss on GraphN (reverse over reverse), full C4 shapes
+    try:
+        X = ctx.random((B_TOTAL, D), 5, normal=True, a=0.0, b=1.0)
+        T = ctx.random((B_TOTAL, D), 9, normal=True, a=0.0, b=1.0)
+        Ws = [ctx.random((D, D), 6 + l, normal=True, a=0.0, b=1.0 / np.sqrt(D)) for l in range(L)]
+        bs = [ctx.array(np.full((1, D), 0.01, np.float32)) for _ in range(L)]
+        vs = [ctx.random((D, D), 10 + l, normal=True, a=0.0, b=1.0) for l in range(L)]
+        hv = {}
+
+        def hvp():
+            hv["r"] = wl.mlp_hvp(ctx, X, Ws, bs, T, vs)
+
+        for _ in range(2):
+            hvp()
+        ctx.profile_begin()
+        ms_hvp = ev_time(hvp, 5)
+        prof = ctx.profile_end()
+        gemms = prof["matmul"]["launches"] / 5
+        out["hvp"] = {"metric": "MLP loss Hessian-vector products/s", "workload": f"C5 GraphN reverse-over-reverse, B={B_TOTAL}, D={D}, L={L}, f32",
+                      "value": 1000.0 / ms_hvp, "unit": "HVPs/s", "ms_per_hvp": ms_hvp, "tape_nodes": int(hv["r"][2]), "gemms_per_hvp": gemms,
+                      "logical_tflop_per_hvp": gemms * 2.0 * B_TOTAL * D * D / 1e12,
+                      "gemm_ms_per_hvp": prof["matmul"]["ms"] / 5}
+    except Exception as e:
+        out["hvp"] = {"error": repr(e)}
     return out
 
 

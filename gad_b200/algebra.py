@@ -616,10 +616,15 @@ class Graph1(_DeviceAlgebra):
         _check(self.lib.gadcu_evaluate_gradients(self.handle, gid.arena, gid.index, seed.handle, 0, C.byref(h)))
         return Store(self.ctx, h, values=False)
 
-    def evaluate_gradients_once(self, gid: GradientId, gradient) -> Store:  # graph.rs:279-290
+    def evaluate_gradients_once(self, gid: GradientId, gradient, comm: Optional["Comm"] = None) -> Store:  # graph.rs:279-290
+        """With `comm`: the sweep of one batch shard — every variable's gradient is summed over the ranks as soon as
+        the sweep has completed it (gadcu_evaluate_gradients_dp), overlapping the rest of the sweep."""
         h = C.c_void_p()
         seed = self._seed(gradient)
-        _check(self.lib.gadcu_evaluate_gradients(self.handle, gid.arena, gid.index, seed.handle, 1, C.byref(h)))
+        if comm is not None and comm.nranks > 1:
+            _check(self.lib.gadcu_evaluate_gradients_dp(self.handle, gid.arena, gid.index, seed.handle, 1, comm.handle, C.byref(h)))
+        else:
+            _check(self.lib.gadcu_evaluate_gradients(self.handle, gid.arena, gid.index, seed.handle, 1, C.byref(h)))
         return Store(self.ctx, h, values=False)
 
     def make_node(self, data: CuArray, inputs: Sequence[Value], vjp) -> Value:
@@ -755,6 +760,14 @@ class Comm:
     def allreduce_sum(self, arrays: Sequence[CuArray]) -> None:
         arr = (C.c_void_p * len(arrays))(*[a.handle for a in arrays])
         _check(self.ctx.lib.gadcu_comm_allreduce_sum(self.handle, arr, len(arrays)))
+
+    def allreduce_sum_async(self, arrays: Sequence[CuArray]) -> None:
+        """On the communicator's stream, after what is already issued on the compute stream; see join()."""
+        arr = (C.c_void_p * len(arrays))(*[a.handle for a in arrays])
+        _check(self.ctx.lib.gadcu_comm_allreduce_sum_async(self.handle, arr, len(arrays)))
+
+    def join(self) -> None:
+        _check(self.ctx.lib.gadcu_comm_join(self.handle))
 
     def __del__(self):
         try:

@@ -318,10 +318,16 @@ class GraphAlgebra final : public Algebra {
   Value make_custom(ArrayRef data, std::vector<Id> inputs, std::shared_ptr<CustomVjp> vjp);
 
   // graph.rs:263-290 / 307-318
+  // Called during a Graph1 sweep with each VARIABLE's gradient as soon as no unprocessed node can contribute to it
+  // any more (and, at the end, for the variables the sweep never completed): the data-parallel sweep starts the
+  // all-reduce of a layer's weight gradient while the layers below are still being differentiated.
+  using FinalHook = std::function<void(Id, const ArrayRef&)>;
+  void set_final_hook(FinalHook h) { final_hook_ = std::move(h); }
   std::unique_ptr<Store> evaluate_gradients(Id id, ArrayRef seed, bool once);
   std::unique_ptr<Store> compute_gradients(Id id, const Value& seed);
 
  private:
+  FinalHook final_hook_;
   std::unique_ptr<Store> sweep(Algebra& ga, Id gid, Value gradient, bool once);
   void vjp(const Node& n, Algebra& ga, Store& store, const Value& g);
 

@@ -64,6 +64,8 @@ struct gadcu_comm {
   gadcu_ctx* ctx = nullptr;
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
+  cudaStream_t stream = nullptr;  // collectives that overlap the compute stream
+  uint64_t pending = 0;           // async collectives issued since the last join
 };
 
 using namespace gadcu;
@@ -89,6 +91,9 @@ gadcu_status gadcu_comm_init(gadcu_ctx* ctx, int nranks, int rank, const void* i
       ncclUniqueId id;
       std::memcpy(&id, id_128_bytes, sizeof(id));
       nccl_check(nccl().CommInitRank(&c->comm, nranks, id, rank), "ncclCommInitRank");
+      int lo = 0, hi = 0;
+      GADCU_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      GADCU_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));  // collectives first when SMs free up
     }
     *out = c.release();
   });
@@ -116,9 +121,86 @@ gadcu_status gadcu_comm_allreduce_sum(gadcu_comm* comm, gadcu_array* const* arra
   });
 }
 
+namespace {
+
+// One array's in-place sum over ranks on the communicator's own stream, ordered after everything already issued on
+// the compute stream (the kernels that produced the array) but not before what is issued afterwards.
+void allreduce_async(gadcu_comm* comm, const ArrayRef& a_in) {
+  ArrayRef a = a_in;
+  if (a->symbolic()) materialize(a);
+  if (a->lazy() || a->symbolic()) fail(GADCU_ERR_INVALID, "allreduce needs dense arrays");
+  gadcu_ctx* ctx = comm->ctx;
+  lazy_before_write(ctx, a->ptr());
+  a->buf->mutated();
+  cudaEvent_t ev;
+  GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  GADCU_CUDA(cudaEventRecord(ev, ctx->stream));
+  GADCU_CUDA(cudaStreamWaitEvent(comm->stream, ev, 0));
+  GADCU_CUDA(cudaEventDestroy(ev));
+  nccl_check(nccl().AllReduce(a->ptr(), a->ptr(), a->elements(), a->dtype == GADCU_F32 ? ncclFloat32 : ncclFloat64, ncclSum, comm->comm,
+                              comm->stream),
+             "ncclAllReduce");
+  comm->pending++;
+  ctx->comm_inflight.store(true, std::memory_order_relaxed);
+  ctx->count_launch();
+}
+
+// The compute stream waits (on the device) for every async collective issued so far.
+void join(gadcu_comm* comm) {
+  if (comm->pending == 0) return;
+  gadcu_ctx* ctx = comm->ctx;
+  cudaEvent_t ev;
+  GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  GADCU_CUDA(cudaEventRecord(ev, comm->stream));
+  GADCU_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
+  GADCU_CUDA(cudaEventDestroy(ev));
+  comm->pending = 0;
+  ctx->comm_inflight.store(false, std::memory_order_relaxed);
+}
+
+}  // namespace
+
+gadcu_status gadcu_comm_allreduce_sum_async(gadcu_comm* comm, gadcu_array* const* arrays, size_t n) {
+  return guard([&] {
+    if (comm->nranks <= 1) return;
+    for (size_t i = 0; i < n; i++) allreduce_async(comm, ArrayRef(arrays[i], true));
+  });
+}
+gadcu_status gadcu_comm_join(gadcu_comm* comm) {
+  return guard([&] {
+    if (comm->nranks > 1) join(comm);
+  });
+}
+
+// Graph1::evaluate_gradients[_once] for a batch shard: each variable's gradient is all-reduced (sum over ranks) as
+// soon as the sweep has completed it — the last layer's weight gradient travels over NVLink while the layers below
+// are still being differentiated — and the compute stream waits for all of them before the call returns.
+gadcu_status gadcu_evaluate_gradients_dp(gadcu_algebra* g, uint32_t arena, uint32_t index, gadcu_array* seed, int once, gadcu_comm* comm,
+                                         gadcu_store** out) {
+  return guard([&] {
+    if (index == 0) fail(GADCU_ERR_MISSING_ID, "Trying to obtain `id` of a constant value.");
+    auto* graph = dynamic_cast<GraphAlgebra*>(g);
+    if (!graph || graph->kind() != GADCU_GRAPH1) fail(GADCU_ERR_INVALID, "evaluate_gradients_dp needs a Graph1 algebra");
+    const bool dp = comm && comm->nranks > 1;
+    if (dp) graph->set_final_hook([comm](Id, const ArrayRef& grad) { allreduce_async(comm, grad); });
+    std::unique_ptr<Store> store;
+    try {
+      store = graph->evaluate_gradients(Id{arena, index}, ArrayRef(seed, true), once != 0);
+    } catch (...) {
+      graph->set_final_hook(nullptr);
+      if (dp) join(comm);
+      throw;
+    }
+    graph->set_final_hook(nullptr);
+    if (dp) join(comm);
+    *out = store.release();
+  });
+}
+
 gadcu_status gadcu_comm_destroy(gadcu_comm* comm) {
   return guard([&] {
     if (!comm) return;
+    if (comm->stream) { cudaStreamSynchronize(comm->stream); cudaStreamDestroy(comm->stream); }
     if (comm->comm) nccl().CommDestroy(comm->comm);
     delete comm;
   });

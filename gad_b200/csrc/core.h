@@ -103,6 +103,7 @@ struct gadcu_ctx {
   bool fuse = true;
   bool strict_reference = false;  // reproduce the reference's matmul VJP for transposed operands as is
   std::atomic<uint64_t> launches{0};
+  std::atomic<bool> comm_inflight{false};  // an overlapped collective is running: GEMMs leave it a few SMs
   std::atomic<uint64_t> epoch{1};
   // deferred elementwise regions (batched.cu): open lane programs by (element count, dtype)
   bool lazy = true;

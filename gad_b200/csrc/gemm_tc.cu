@@ -624,7 +624,11 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   CUtensorMap mah = make_map(ah, a_mn, g.M, g.K, g.lda, 128, BKT, k_swz), mal = make_map(al, a_mn, g.M, g.K, g.lda, 128, BKT, k_swz);
   CUtensorMap mbh = make_map(bh, b_mn, g.N, g.K, g.ldb, 128, BKT, k_swz), mbl = make_map(bl, b_mn, g.N, g.K, g.ldb, 128, BKT, k_swz);
   const uint64_t tiles = (g.M / 256) * (g.N / 256);
-  const uint64_t clusters = std::min<uint64_t>(tiles, uint64_t(ctx->sm_count / 2));
+  // while an overlapped all-reduce is in flight a few SM pairs are left to its CTAs (a persistent CTA per SM would
+  // otherwise keep them out until the GEMM ends)
+  static const uint64_t reserve = [] { const char* e = getenv("GADCU_DP_RESERVE_CLUSTERS"); return e ? uint64_t(atoi(e)) : uint64_t(0); }();
+  const uint64_t usable = uint64_t(ctx->sm_count / 2) - (ctx->comm_inflight.load(std::memory_order_relaxed) ? reserve : 0);
+  const uint64_t clusters = std::min<uint64_t>(tiles, usable);
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<BKT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BKT, S>::kSmem);

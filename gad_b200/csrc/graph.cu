@@ -11,6 +11,8 @@
 #include "algebra.h"
 #include "batched.h"
 
+#include <algorithm>
+
 using namespace gadcu;
 
 // ---- store --------------------------------------------------------------------------------------
@@ -624,6 +626,27 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
   std::priority_queue<Id> heap;  // max-heap: strictly descending ids = reverse topological order
   heap.push(gid);
   Id guard = gid.next_id();
+  // final-gradient hook: how many nodes still have to run before a variable's gradient is complete
+  std::vector<uint32_t> waiting;  // by node index; only variables are counted
+  auto distinct_variable_inputs = [&](const Node& nd, std::vector<uint32_t>& out) {
+    out.clear();
+    for (auto& in : nd.inputs) {
+      if (!in.some() || in.arena != arena_id_ || in.index > nodes_.size()) continue;
+      const Node& src = nodes_[in.index - 1];
+      if (src.op != Op::VARIABLE || src.has_update) continue;
+      if (std::find(out.begin(), out.end(), in.index) == out.end()) out.push_back(in.index);
+    }
+  };
+  std::vector<uint32_t> scratch;
+  if (final_hook_ && ga.is_eval()) {
+    waiting.assign(nodes_.size() + 1, 0);
+    for (auto& nd : nodes_) {
+      if (!nd.has_update) continue;
+      distinct_variable_inputs(nd, scratch);
+      for (uint32_t v : scratch) waiting[v]++;
+    }
+  }
+  std::vector<char> fired(waiting.size(), 0);
   while (!heap.empty()) {
     Id id = heap.top();
     heap.pop();
@@ -652,10 +675,23 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
         vjp(node, ga, *store, g);
       }
     }
+    if (!waiting.empty()) {
+      distinct_variable_inputs(node, scratch);
+      for (uint32_t v : scratch)
+        if (--waiting[v] == 0) {
+          const Value* gv = store->get(Id{arena_id_, v});
+          if (gv && gv->data) { fired[v] = 1; final_hook_(Id{arena_id_, v}, gv->data); }
+        }
+    }
     for (auto& in : node.inputs)
       if (in.some()) heap.push(in);
     if (once) node.clear();
   }
+  if (!waiting.empty())  // variables some unreached node also feeds (or the root itself): complete as far as this sweep goes
+    for (auto& kv : store->values) {
+      const Id vid = kv.first;
+      if (is_variable(vid) && vid.index < fired.size() && !fired[vid.index] && kv.second.data) final_hook_(vid, kv.second.data);
+    }
   return store;
 }
 

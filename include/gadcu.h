@@ -259,6 +259,15 @@ GADCU_API gadcu_status gadcu_batched_program_stats(const gadcu_store* s, uint64_
 GADCU_API gadcu_status gadcu_comm_unique_id(void* out_128_bytes);
 GADCU_API gadcu_status gadcu_comm_init(gadcu_ctx* ctx, int nranks, int rank, const void* id_128_bytes, gadcu_comm** out);
 GADCU_API gadcu_status gadcu_comm_allreduce_sum(gadcu_comm* comm, gadcu_array* const* arrays, size_t n); /* in place */
+/* Overlapped form: the collectives run on the communicator's own stream after everything already issued on the
+ * compute stream; gadcu_comm_join makes the compute stream wait for them (no host synchronisation). */
+GADCU_API gadcu_status gadcu_comm_allreduce_sum_async(gadcu_comm* comm, gadcu_array* const* arrays, size_t n);
+GADCU_API gadcu_status gadcu_comm_join(gadcu_comm* comm);
+/* evaluate_gradients[_once] of one batch shard (net_ext.rs:47-73 sums per-example gradients): every variable's gradient
+ * is all-reduced as soon as the sweep has completed it, overlapping the rest of the sweep; joined before returning.
+ * comm == NULL or a 1-rank communicator: identical to gadcu_evaluate_gradients. */
+GADCU_API gadcu_status gadcu_evaluate_gradients_dp(gadcu_algebra* g, uint32_t arena, uint32_t index, gadcu_array* seed, int once,
+                                                   gadcu_comm* comm, gadcu_store** out);
 GADCU_API gadcu_status gadcu_comm_destroy(gadcu_comm* comm);
 
 #ifdef __cplusplus
