@@ -204,7 +204,8 @@ def run_ours(args):
         dist.broadcast_object_list(obj, src=0)
         comm = gb.Comm(ctx, world, rank, obj[0])
 
-    rows = B_TOTAL // world
+    from gad_b200 import dp
+    rows = dp.even_rows(B_TOTAL, world)
     # synthetic data of the named shapes: X~N(0,1) seed 5, W_l~N(0,1/D) seeds 6-8, b=0.01, target~N(0,1) seed 9
     X = ctx.random((rows, D), 5 + 100 * rank, normal=True, a=0.0, b=1.0)
     T = ctx.random((rows, D), 9 + 100 * rank, normal=True, a=0.0, b=1.0)
