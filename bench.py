@@ -240,7 +240,7 @@ def run_ours(args):
 
     keep = {}
 
-    overlap = os.environ.get("GADCU_DP_OVERLAP", "0") == "1"  # measured slower on 2x B200: DESIGN.md §8
+    overlap = os.environ.get("GADCU_DP_OVERLAP", "1") == "1"  # fused GEMM -> reduce-scatter over peer memory
 
     def step_resident():
         keep["out"] = wl.mlp_step(ctx, X, Ws, bs, T, comm, overlap)
@@ -323,7 +323,7 @@ def run_ours(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C4 3-layer tanh MLP {D}-wide, batch {B_TOTAL}, f32, Graph1 fwd + reverse sweep", "global_batch": B_TOTAL,
-                       "rows_per_gpu": rows, "parallelism": f"dp{world} (batch rows sharded, NCCL allreduce of weight grads" + (", overlapped with the sweep)" if overlap and world > 1 else ")"),
+                       "rows_per_gpu": rows, "parallelism": f"dp{world} (batch rows sharded, NCCL allreduce of weight grads" + (": dW GEMM epilogues reduce-scatter over NVLink peer memory, gather overlapped with the sweep)" if overlap and world > 1 else ")"),
                        "l2": "inputs larger than L2 (activations 128 MiB, weights 64 MiB each vs 126 MB L2)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "kernel_time_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}, "host_issue_ms_per_step": host_issue_ms,

@@ -323,13 +323,23 @@ class GraphAlgebra final : public Algebra {
   // all-reduce of a layer's weight gradient while the layers below are still being differentiated.
   using FinalHook = std::function<void(Id, const ArrayRef&)>;
   void set_final_hook(FinalHook h) { final_hook_ = std::move(h); }
+  // Asked by the matmul VJP when the product it is about to compute is the ONLY contribution to a variable's
+  // gradient: may compute it itself (the data-parallel GEMM whose epilogue reduce-scatters over NVLink) and return
+  // the array that will hold the rank-summed gradient, or return null to decline. The final hook is not called for
+  // a variable served this way.
+  using GemmSink = std::function<ArrayRef(Id, const ArrayRef& lhs, const ArrayRef& rhs, MatProp pl, MatProp pr)>;
+  void set_gemm_sink(GemmSink h) { gemm_sink_ = std::move(h); }
   std::unique_ptr<Store> evaluate_gradients(Id id, ArrayRef seed, bool once);
   std::unique_ptr<Store> compute_gradients(Id id, const Value& seed);
 
  private:
   FinalHook final_hook_;
+  GemmSink gemm_sink_;
+  std::vector<uint32_t> waiting_;  // during a hooked sweep: nodes still to run before a variable's gradient is complete
+  std::vector<char> served_;       // variables whose gradient a GemmSink produced
   std::unique_ptr<Store> sweep(Algebra& ga, Id gid, Value gradient, bool once);
   void vjp(const Node& n, Algebra& ga, Store& store, const Value& g);
+  ArrayRef try_gemm_sink(Id id, const ArrayRef& lhs, const ArrayRef& rhs, MatProp pl, MatProp pr);
 
   bool higher_order_;
   gadcu_algebra_kind kind_override_ = gadcu_algebra_kind(0);

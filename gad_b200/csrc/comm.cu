@@ -8,7 +8,10 @@
 // already mapped by the host process (e.g. torch's) instead of loading a second copy.
 #include <dlfcn.h>
 
+#include <algorithm>
+#include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "algebra.h"
 #include "batched.h"
@@ -27,6 +30,7 @@ struct Nccl {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -46,6 +50,7 @@ Nccl& nccl() {
     n.CommInitRank = reinterpret_cast<decltype(n.CommInitRank)>(dlsym(n.lib, "ncclCommInitRank"));
     n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(dlsym(n.lib, "ncclCommDestroy"));
     n.AllReduce = reinterpret_cast<decltype(n.AllReduce)>(dlsym(n.lib, "ncclAllReduce"));
+    n.AllGather = reinterpret_cast<decltype(n.AllGather)>(dlsym(n.lib, "ncclAllGather"));
     n.GroupStart = reinterpret_cast<decltype(n.GroupStart)>(dlsym(n.lib, "ncclGroupStart"));
     n.GroupEnd = reinterpret_cast<decltype(n.GroupEnd)>(dlsym(n.lib, "ncclGroupEnd"));
     n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(dlsym(n.lib, "ncclGetErrorString"));
@@ -60,12 +65,42 @@ void nccl_check(ncclResult_t r, const char* what) {
 
 }  // namespace
 
+// ---- symmetric peer memory for the fused GEMM -> reduce-scatter -> all-gather exchange ---------------------
+// One cudaMalloc per rank, opened by every other rank through CUDA IPC (handles travel through an NCCL all-gather):
+//   [ flags: 2 x 32 x u32 | small: 2 x 8 x kSmallBytes | staging: kSlots x slot_bytes | result: kSlots x slot_bytes ]
+// staging[slot] receives, for every tile this rank owns, the nranks partial tiles (pushed by the GEMM epilogues of all
+// ranks); result[slot] receives the reduced gradient in its final column-major layout (pushed by every owner);
+// small[parity][r] receives rank r's copy of a batch of small arrays (biases, the loss) to be summed locally.
+// Barriers issued on the communicator's stream and on the compute stream count separately (flag set 0 / 1).
+constexpr int kSlots = 3;
+constexpr size_t kSmallBytes = 256 * 1024;
+constexpr size_t kHeapHeader = 256 + 2 * 8 * kSmallBytes;
+struct SymmHeap {
+  size_t slot_bytes = 0;
+  void* local = nullptr;
+  void* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // peer[rank] == local
+  uint32_t* flags(int r, int set) const { return static_cast<uint32_t*>(peer[r]) + 32 * set; }
+  float* small(int r, int parity, int src) const {
+    return reinterpret_cast<float*>(static_cast<char*>(peer[r]) + 256 + (size_t(parity) * 8 + size_t(src)) * kSmallBytes);
+  }
+  float* staging(int r, int slot) const { return reinterpret_cast<float*>(static_cast<char*>(peer[r]) + kHeapHeader + size_t(slot) * slot_bytes); }
+  float* result(int r, int slot) const { return reinterpret_cast<float*>(static_cast<char*>(peer[r]) + kHeapHeader + size_t(kSlots + slot) * slot_bytes); }
+};
+
 struct gadcu_comm {
   gadcu_ctx* ctx = nullptr;
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
   cudaStream_t stream = nullptr;  // collectives that overlap the compute stream
   uint64_t pending = 0;           // async collectives issued since the last join
+  SymmHeap heap;
+  uint64_t exchanges = 0;         // fused exchanges so far (slot = exchanges % kSlots)
+  uint32_t barriers[2] = {0, 0};  // cross-rank barriers so far on the communicator's / the compute stream
+  uint64_t small_calls = 0;       // small all-reduces so far (parity of the buffer)
+  cudaEvent_t slot_done[kSlots] = {nullptr, nullptr, nullptr};
+  std::vector<gadcu::ArrayRef> deferred;  // small gradients: one grouped NCCL all-reduce at the join
+  bool no_peer_memory = false;    // CUDA IPC / peer access unavailable: everything goes through NCCL
+  std::vector<std::pair<const char*, cudaEvent_t>> trace;  // GADCU_DP_TRACE=1: timeline of one step
 };
 
 using namespace gadcu;
@@ -99,11 +134,18 @@ gadcu_status gadcu_comm_init(gadcu_ctx* ctx, int nranks, int rank, const void* i
   });
 }
 
+namespace {
+bool small_allreduce(gadcu_comm* comm, gadcu_array* const* arrays, size_t n);
+}
+
 // In-place sum over ranks of every array, issued as one NCCL group on the context's stream (so it
 // is ordered after the kernels that produced the gradients and before their consumers).
 gadcu_status gadcu_comm_allreduce_sum(gadcu_comm* comm, gadcu_array* const* arrays, size_t n) {
   return guard([&] {
     if (comm->nranks <= 1) return;
+    for (size_t i = 0; i < n; i++)
+      if (arrays[i]->symbolic()) materialize(ArrayRef(arrays[i], true));
+    if (small_allreduce(comm, arrays, n)) return;  // once the peer-memory exchange is up, small arrays use it too
     Nccl& nc = nccl();
     nccl_check(nc.GroupStart(), "ncclGroupStart");
     for (size_t i = 0; i < n; i++) {
@@ -122,6 +164,259 @@ gadcu_status gadcu_comm_allreduce_sum(gadcu_comm* comm, gadcu_array* const* arra
 }
 
 namespace {
+
+// ---- kernels of the fused exchange ----------------------------------------------------------------------
+// Cross-GPU barrier number `seq` (1, 2, ...): thread r tells rank r "I am here" and waits for rank r to say the same.
+// Everything this GPU wrote to peer memory before the barrier is visible to the peers after it.
+struct PeerFlags { uint32_t* p[8]; };
+__global__ void dp_barrier_kernel(PeerFlags flags, int nranks, int rank, uint32_t seq) {
+  const int r = threadIdx.x;
+  if (r < nranks) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[r] + rank), "r"(seq) : "memory");
+    uint32_t seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags.p[rank] + r) : "memory");
+    } while (seen < seq);
+    __threadfence_system();
+  }
+}
+
+// Owner side of the reduce-scatter + the all-gather: for every tile this rank owns, add the nranks partial tiles in
+// rank order (deterministic) and store the sum into every rank's result buffer at the tile's place in the
+// column-major [M, N] gradient. 128-bit accesses; the peer stores travel over NVLink.
+struct PeerResults { float* p[8]; };
+__global__ void __launch_bounds__(256) dp_reduce_publish_kernel(const float4* __restrict__ staging, PeerResults results, uint32_t M,
+                                                                uint32_t num_mt, uint32_t tiles, uint32_t nranks, uint32_t rank) {
+  const uint32_t owned = tiles > rank ? (tiles - rank + nranks - 1) / nranks : 0;
+  const uint64_t total = uint64_t(owned) * 16384u;  // float4s
+  for (uint64_t i = uint64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += uint64_t(gridDim.x) * 256) {
+    const uint32_t k = uint32_t(i >> 14), v = uint32_t(i & 16383u);
+    const float4* part = staging + (uint64_t(k) * nranks) * 16384u + v;
+    float4 acc = part[0];
+    for (uint32_t r = 1; r < nranks; r++) {
+      const float4 x = part[uint64_t(r) * 16384u];
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    const uint32_t t = k * nranks + rank, mt = t % num_mt, nt = t / num_mt;
+    const uint32_t row = (v * 4u) & 255u, col = (v * 4u) >> 8;
+    const uint64_t off = uint64_t(nt * 256u + col) * M + mt * 256u + row;
+    for (uint32_t d = 0; d < nranks; d++) *reinterpret_cast<float4*>(results.p[d] + off) = acc;
+  }
+}
+
+void ensure_heap(gadcu_comm* comm, size_t bytes) {
+  if (comm->heap.slot_bytes >= bytes) return;
+  if (comm->heap.local) {  // sized by the first gradient that came through; a larger one later goes through NCCL
+    throw GadError(GADCU_ERR_UNSUPPORTED, "gradient larger than the symmetric heap");
+  }
+  if (comm->nranks > 8) fail(GADCU_ERR_UNSUPPORTED, "data-parallel exchange: at most 8 ranks");
+  gadcu_ctx* ctx = comm->ctx;
+  Nccl& nc = nccl();
+  if (!nc.AllGather) fail(GADCU_ERR_NCCL, "ncclAllGather is not available");
+  SymmHeap& h = comm->heap;
+  h.slot_bytes = (bytes + 255) / 256 * 256;
+  const size_t total = kHeapHeader + size_t(2 * kSlots) * h.slot_bytes;
+  GADCU_CUDA(cudaMalloc(&h.local, total));
+  GADCU_CUDA(cudaMemsetAsync(h.local, 0, 256, ctx->stream));
+  // exchange the IPC handles through NCCL (every rank calls this at the same point of the same step)
+  cudaIpcMemHandle_t mine;
+  GADCU_CUDA(cudaIpcGetMemHandle(&mine, h.local));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  char* dev = nullptr;
+  GADCU_CUDA(cudaMalloc(&dev, 64 * size_t(comm->nranks + 1)));
+  GADCU_CUDA(cudaMemcpyAsync(dev, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+  nccl_check(nc.AllGather(dev, dev + 64, 64, /*ncclUint8*/ 1, comm->comm, ctx->stream), "ncclAllGather");
+  std::vector<cudaIpcMemHandle_t> all(comm->nranks);
+  GADCU_CUDA(cudaMemcpyAsync(all.data(), dev + 64, 64 * size_t(comm->nranks), cudaMemcpyDeviceToHost, ctx->stream));
+  GADCU_CUDA(cudaStreamSynchronize(ctx->stream));
+  GADCU_CUDA(cudaFree(dev));
+  for (int r = 0; r < comm->nranks; r++) {
+    if (r == comm->rank) { h.peer[r] = h.local; continue; }
+    GADCU_CUDA(cudaIpcOpenMemHandle(&h.peer[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+  }
+  for (int s = 0; s < kSlots; s++) GADCU_CUDA(cudaEventCreateWithFlags(&comm->slot_done[s], cudaEventDisableTiming));
+}
+
+bool tracing() {
+  static const bool on = getenv("GADCU_DP_TRACE") != nullptr;
+  return on;
+}
+void mark(gadcu_comm* comm, const char* what, cudaStream_t stream) {
+  if (!tracing()) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, stream);
+  comm->trace.emplace_back(what, e);
+}
+void dump_trace(gadcu_comm* comm) {
+  if (!tracing() || comm->trace.empty()) return;
+  cudaStreamSynchronize(comm->stream);
+  cudaStreamSynchronize(comm->ctx->stream);
+  static int dumps = 0;
+  const bool print = ++dumps == 6;
+  for (auto& t : comm->trace) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, comm->trace.front().second, t.second);
+    if (print) fprintf(stderr, "[dp trace r%d] %-32s %8.3f ms\n", comm->rank, t.first, ms);
+  }
+  for (auto& t : comm->trace) cudaEventDestroy(t.second);
+  comm->trace.clear();
+}
+
+void barrier_on(gadcu_comm* comm, cudaStream_t stream) {
+  const int set = stream == comm->stream ? 0 : 1;
+  PeerFlags f;
+  for (int r = 0; r < 8; r++) f.p[r] = r < comm->nranks ? comm->heap.flags(r, set) : nullptr;
+  dp_barrier_kernel<<<1, 32, 0, stream>>>(f, comm->nranks, comm->rank, ++comm->barriers[set]);
+  comm->ctx->count_launch();
+}
+
+// ---- small arrays (bias gradients, the loss): push a packed copy to every rank, barrier, sum in rank order ----------
+struct SmallList {
+  float* ptr[16];
+  uint32_t n[16];
+  uint32_t count, total;
+};
+struct PeerSmall { float* p[8]; };
+__global__ void __launch_bounds__(256) dp_small_push_kernel(SmallList list, PeerSmall dst, uint32_t nranks) {
+  uint32_t base = 0;
+  for (uint32_t a = 0; a < list.count; a++) {
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < list.n[a]; i += gridDim.x * 256) {
+      const float v = list.ptr[a][i];
+      for (uint32_t d = 0; d < nranks; d++) dst.p[d][base + i] = v;
+    }
+    base += list.n[a];
+  }
+}
+__global__ void __launch_bounds__(256) dp_small_sum_kernel(SmallList list, const float* __restrict__ parts, uint32_t nranks) {
+  uint32_t base = 0;
+  for (uint32_t a = 0; a < list.count; a++) {
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < list.n[a]; i += gridDim.x * 256) {
+      float acc = parts[base + i];
+      for (uint32_t r = 1; r < nranks; r++) acc += parts[size_t(r) * (kSmallBytes / 4) + base + i];
+      list.ptr[a][i] = acc;
+    }
+    base += list.n[a];
+  }
+}
+// true if it handled them (f32, dense, few and small, and the symmetric heap exists)
+bool small_allreduce(gadcu_comm* comm, gadcu_array* const* arrays, size_t n) {
+  if (tracing() && comm->rank == 0) {
+    fprintf(stderr, "[dp trace] small_allreduce: heap %p n %zu:", comm->heap.local, n);
+    for (size_t i = 0; i < n; i++)
+      fprintf(stderr, " [%s dt%d lazy%d sym%d]", arrays[i]->dims.str().c_str(), int(arrays[i]->dtype), int(arrays[i]->lazy()), int(arrays[i]->symbolic()));
+    fprintf(stderr, "\n");
+  }
+  if (!comm->heap.local || n == 0 || n > 16) return false;
+  SmallList list{};
+  for (size_t i = 0; i < n; i++) {
+    gadcu_array* a = arrays[i];
+    if (a->dtype != GADCU_F32 || a->lazy() || a->symbolic()) return false;
+    list.ptr[i] = static_cast<float*>(a->ptr());
+    list.n[i] = uint32_t(a->elements());
+    list.total += uint32_t(a->elements());
+  }
+  if (size_t(list.total) * 4 > kSmallBytes) return false;
+  list.count = uint32_t(n);
+  gadcu_ctx* ctx = comm->ctx;
+  for (size_t i = 0; i < n; i++) {
+    lazy_before_write(ctx, arrays[i]->ptr());
+    arrays[i]->buf->mutated();
+  }
+  const int parity = int(comm->small_calls++ & 1);
+  PeerSmall dst;
+  for (int r = 0; r < 8; r++) dst.p[r] = r < comm->nranks ? comm->heap.small(r, parity, comm->rank) : nullptr;
+  const unsigned grid = unsigned(std::min<uint32_t>((list.total + 255) / 256, 64));
+  mark(comm, "small: start", ctx->stream);
+  dp_small_push_kernel<<<grid, 256, 0, ctx->stream>>>(list, dst, uint32_t(comm->nranks));
+  mark(comm, "small: pushed", ctx->stream);
+  barrier_on(comm, ctx->stream);
+  mark(comm, "small: barrier done", ctx->stream);
+  dp_small_sum_kernel<<<grid, 256, 0, ctx->stream>>>(list, comm->heap.small(comm->rank, parity, 0), uint32_t(comm->nranks));
+  mark(comm, "small: summed", ctx->stream);
+  ctx->count_launch(2);
+  return true;
+}
+
+// The matmul VJP's product IS a variable's gradient: compute it with the tile-pushing epilogue and run the rest of
+// the exchange on the communicator's stream. Returns the array that holds the rank-summed gradient after the join.
+ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, MatProp p1, MatProp p2) {
+  gadcu_ctx* ctx = comm->ctx;
+  if (a_in->dtype != GADCU_F32 || b_in->dtype != GADCU_F32) return ArrayRef();
+  const Dim4 rd = check::matmul(a_in->dims, b_in->dims, p1, p2);
+  if (rd[2] * rd[3] != 1) return ArrayRef();
+  ArrayRef a = materialize(a_in), b = materialize(b_in);
+  k::GemmArgs g;
+  g.dt = GADCU_F32;
+  g.A = a->ptr();
+  g.B = b->ptr();
+  g.M = rd[0];
+  g.N = rd[1];
+  g.K = p1.transposed ? a->dims[0] : a->dims[1];
+  g.ta = p1.transposed;
+  g.tb = p2.transposed;
+  g.lda = a->dims[0];
+  g.ldb = b->dims[0];
+  g.strideC = rd[0] * rd[1];
+  if (a->ptr() == a->buf->ptr) g.a_buf = a->buf.get();
+  if (b->ptr() == b->buf->ptr) g.b_buf = b->buf.get();
+  if (!k::gemm_push_supported(g) || comm->no_peer_memory) return ArrayRef();
+  const size_t bytes = size_t(g.M) * g.N * 4;
+  try {
+    ensure_heap(comm, bytes);
+  } catch (const GadError& e) {
+    // no peer memory on this system (IPC disabled, no P2P): decline — the gradient then travels through the grouped
+    // NCCL all-reduce at the end of the sweep like the small ones. Systemic, so every rank takes the same branch.
+    fprintf(stderr, "gadcu: peer-memory gradient exchange unavailable (%s); using NCCL\n", e.msg.c_str());
+    cudaGetLastError();
+    comm->no_peer_memory = true;
+    return ArrayRef();
+  }
+  const int slot = int(comm->exchanges % kSlots);
+  // the slot's previous exchange (three exchanges ago) must have been copied out here before anyone may push into it
+  // again: peers push only after passing a barrier that this rank enters after this wait
+  if (comm->exchanges >= uint64_t(kSlots)) GADCU_CUDA(cudaStreamWaitEvent(ctx->stream, comm->slot_done[slot], 0));
+  comm->exchanges++;
+  k::GemmPush push;
+  push.nranks = uint32_t(comm->nranks);
+  push.rank = uint32_t(comm->rank);
+  for (int r = 0; r < comm->nranks; r++) push.peer[r] = comm->heap.staging(r, slot);
+  g.push = &push;
+  ArrayRef out = new_array(ctx, GADCU_F32, rd);
+  g.C = out->ptr();
+  mark(comm, "compute: gemm start", ctx->stream);
+  k::launch_gemm(ctx, g);  // compute stream: partial tiles land in their owners' staging buffers
+  mark(comm, "compute: gemm end", ctx->stream);
+  cudaEvent_t ev;
+  GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  GADCU_CUDA(cudaEventRecord(ev, ctx->stream));
+  GADCU_CUDA(cudaStreamWaitEvent(comm->stream, ev, 0));
+  GADCU_CUDA(cudaEventDestroy(ev));
+  // communicator stream, overlapping the rest of the sweep: all partials have arrived -> reduce + publish -> all
+  // results have arrived -> copy out
+  mark(comm, "comm: after gemm", comm->stream);
+  barrier_on(comm, comm->stream);
+  mark(comm, "comm: barrier 1 done", comm->stream);
+  const uint32_t num_mt = uint32_t(g.M / 256), tiles = num_mt * uint32_t(g.N / 256);
+  PeerResults res;
+  for (int r = 0; r < 8; r++) res.p[r] = r < comm->nranks ? comm->heap.result(r, slot) : nullptr;
+  const uint32_t owned = tiles > uint32_t(comm->rank) ? (tiles - comm->rank + comm->nranks - 1) / comm->nranks : 0;
+  if (owned > 0) {
+    const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(owned) * 64, uint64_t(ctx->sm_count) * 4));
+    dp_reduce_publish_kernel<<<grid, 256, 0, comm->stream>>>(reinterpret_cast<const float4*>(comm->heap.staging(comm->rank, slot)), res,
+                                                             uint32_t(g.M), num_mt, tiles, uint32_t(comm->nranks), uint32_t(comm->rank));
+    ctx->count_launch();
+  }
+  mark(comm, "comm: reduce+publish done", comm->stream);
+  barrier_on(comm, comm->stream);
+  mark(comm, "comm: barrier 2 done", comm->stream);
+  GADCU_CUDA(cudaMemcpyAsync(out->ptr(), comm->heap.result(comm->rank, slot), bytes, cudaMemcpyDeviceToDevice, comm->stream));
+  mark(comm, "comm: copy out done", comm->stream);
+  GADCU_CUDA(cudaEventRecord(comm->slot_done[slot], comm->stream));
+  comm->pending++;
+  return out;
+}
 
 // One array's in-place sum over ranks on the communicator's own stream, ordered after everything already issued on
 // the compute stream (the kernels that produced the array) but not before what is issued afterwards.
@@ -182,17 +477,49 @@ gadcu_status gadcu_evaluate_gradients_dp(gadcu_algebra* g, uint32_t arena, uint3
     auto* graph = dynamic_cast<GraphAlgebra*>(g);
     if (!graph || graph->kind() != GADCU_GRAPH1) fail(GADCU_ERR_INVALID, "evaluate_gradients_dp needs a Graph1 algebra");
     const bool dp = comm && comm->nranks > 1;
-    if (dp) graph->set_final_hook([comm](Id, const ArrayRef& grad) { allreduce_async(comm, grad); });
+    // GADCU_DP = fused (default): GEMM-produced gradients are reduce-scattered by the GEMM epilogue over peer memory
+    // and gathered on the communicator's stream while the sweep continues; everything else (biases) goes through
+    // one grouped NCCL all-reduce at the end. GADCU_DP = nccl-overlap: every gradient through NCCL as soon as final.
+    static const int mode = [] {
+      const char* e = getenv("GADCU_DP");
+      return e && std::string(e) == "nccl-overlap" ? 1 : 0;
+    }();
+    if (dp) {
+      if (mode == 1) {
+        graph->set_final_hook([comm](Id, const ArrayRef& grad) { allreduce_async(comm, grad); });
+      } else {
+        graph->set_final_hook([comm](Id, const ArrayRef& grad) { comm->deferred.push_back(grad); });
+        graph->set_gemm_sink([comm](Id, const ArrayRef& lhs, const ArrayRef& rhs, MatProp pl, MatProp pr) { return dp_gemm(comm, lhs, rhs, pl, pr); });
+      }
+    }
+    auto finish = [&] {
+      graph->set_final_hook(nullptr);
+      graph->set_gemm_sink(nullptr);
+      if (!dp) return;
+      if (!comm->deferred.empty()) {
+        std::vector<gadcu_array*> raw;
+        for (auto& a : comm->deferred) raw.push_back(a.get());
+        mark(comm, "compute: before nccl(deferred)", comm->ctx->stream);
+        gadcu_status st = gadcu_comm_allreduce_sum(comm, raw.data(), raw.size());
+        mark(comm, "compute: after nccl(deferred)", comm->ctx->stream);
+        comm->deferred.clear();
+        if (st != GADCU_OK) fail(st, last_error());
+      }
+      join(comm);
+    };
     std::unique_ptr<Store> store;
+    if (dp) mark(comm, "compute: sweep start", comm->ctx->stream);
     try {
       store = graph->evaluate_gradients(Id{arena, index}, ArrayRef(seed, true), once != 0);
     } catch (...) {
-      graph->set_final_hook(nullptr);
-      if (dp) join(comm);
+      comm->deferred.clear();
+      try { finish(); } catch (...) {}
       throw;
     }
-    graph->set_final_hook(nullptr);
-    if (dp) join(comm);
+    if (dp) mark(comm, "compute: sweep issued", comm->ctx->stream);
+    finish();
+    if (dp) mark(comm, "compute: joined", comm->ctx->stream);
+    if (dp) dump_trace(comm);
     *out = store.release();
   });
 }
@@ -201,6 +528,11 @@ gadcu_status gadcu_comm_destroy(gadcu_comm* comm) {
   return guard([&] {
     if (!comm) return;
     if (comm->stream) { cudaStreamSynchronize(comm->stream); cudaStreamDestroy(comm->stream); }
+    for (int r = 0; r < comm->nranks; r++)
+      if (comm->heap.peer[r] && r != comm->rank) cudaIpcCloseMemHandle(comm->heap.peer[r]);
+    if (comm->heap.local) cudaFree(comm->heap.local);
+    for (auto& e : comm->slot_done)
+      if (e) cudaEventDestroy(e);
     if (comm->comm) nccl().CommDestroy(comm->comm);
     delete comm;
   });

@@ -363,7 +363,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                         const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, float* __restrict__ C,
                         uint32_t M, uint32_t N, uint32_t K, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t accumulate,
-                        OperandLayout la, OperandLayout lb, uint32_t band_m) {
+                        OperandLayout la, OperandLayout lb, uint32_t band_m, const GemmPush push) {
   using cfg = Cfg2<BKT, S>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -483,20 +483,35 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
       const uint32_t as = ti & 1, use = ti >> 1;
       mbar_wait(tmem_full_bar(as), use & 1);
       tc_fence_after();
-      const uint32_t row = mt * 256 + rank * 128 + q * 32 + lane;
-      float* crow = C + row + size_t(nt) * 256 * M;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * kAccCols;
+      if (push.nranks) {
+        // fused reduce-scatter: this rank's partial tile goes to the staging buffer of the tile's owner, as a dense
+        // 256 x 256 block (a warp store = 32 consecutive rows = 128 contiguous bytes over NVLink)
+        const uint32_t tl = nt * sched.num_mt + mt;
+        float* dst = push.peer[tl % push.nranks] + (size_t(tl / push.nranks) * push.nranks + push.rank) * 65536u + rank * 128 + q * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < 256; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + uint32_t(c), r);
-        tmem_ld_wait();
+        for (int c = 0; c < 256; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + uint32_t(c), r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          float* p = crow + size_t(c + j) * M;
-          float v = __uint_as_float(r[j]);
-          if (accumulate) v = *p + v;  // store.rs:52 `current + new`, fused into the epilogue
-          *p = v;
+          for (int j = 0; j < 32; j++) dst[size_t(c + j) * 256] = __uint_as_float(r[j]);
+        }
+      } else {
+        const uint32_t row = mt * 256 + rank * 128 + q * 32 + lane;
+        float* crow = C + row + size_t(nt) * 256 * M;
+#pragma unroll 1
+        for (int c = 0; c < 256; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + uint32_t(c), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            float* p = crow + size_t(c + j) * M;
+            float v = __uint_as_float(r[j]);
+            if (accumulate) v = *p + v;  // store.rs:52 `current + new`, fused into the epilogue
+            *p = v;
+          }
         }
       }
       tc_fence_before();
@@ -634,7 +649,8 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
     cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<BKT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BKT, S>::kSmem);
   });
   gemm_tf32x3_pair_kernel<BKT, S><<<unsigned(2 * clusters), kThreads2, Cfg2<BKT, S>::kSmem, ctx->stream>>>(
-      mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M), uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb, 8u);
+      mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M), uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb, 8u,
+      g.push ? *g.push : GemmPush{});
 }
 
 int pair_variant() {  // GADCU_GEMM_PAIR = off | 32x3 | 16x6 (default 32x3)
@@ -668,6 +684,10 @@ static const float* split_operand(gadcu_ctx* ctx, const float* x, uint64_t elems
   return hi;
 }
 
+bool gemm_push_supported(const GemmArgs& g) {
+  return gemm_tc_supported(g) && pair_variant() != 0 && g.M % 256 == 0 && g.N % 256 == 0 && !g.accumulate;
+}
+
 void launch_gemm_tc(gadcu_ctx* ctx, const GemmArgs& g) {
   const uint64_t a_elems = g.M * g.K, b_elems = g.K * g.N;
   ArrayRef keep_a, keep_b;
@@ -684,6 +704,7 @@ void launch_gemm_tc(gadcu_ctx* ctx, const GemmArgs& g) {
       default: launch_pair<32, 3>(ctx, g, ah, al, bh, bl, a_mn, b_mn); break;
     }
   } else {
+    if (g.push) fail(GADCU_ERR_UNSUPPORTED, "gemm: the tile-pushing epilogue needs M and N to be multiples of 256");
     const OperandLayout mn_layout{BK * 128u, 512u, 1024u, 1u};
     const OperandLayout k_layout{16u, 1024u, UMMA_K * 4u, 2u};
     const OperandLayout la = a_mn ? mn_layout : k_layout, lb = b_mn ? mn_layout : k_layout;

@@ -239,6 +239,15 @@ Value GraphAlgebra::softmax_as(const Value& v, const Dim4& d) {  // array_compar
   return make_node(r.data, std::move(n));
 }
 
+// The product about to be computed is the whole gradient of variable `id` (no earlier contribution, and the node
+// being differentiated is the last one that feeds it): offer it to the sink.
+ArrayRef GraphAlgebra::try_gemm_sink(Id id, const ArrayRef& lhs, const ArrayRef& rhs, MatProp pl, MatProp pr) {
+  if (!gemm_sink_ || id.arena != arena_id_ || id.index >= waiting_.size() || waiting_[id.index] != 1 || !is_variable(id)) return ArrayRef();
+  ArrayRef out = gemm_sink_(id, lhs, rhs, pl, pr);
+  if (out) served_[id.index] = 1;
+  return out;
+}
+
 // ---- VJPs -----------------------------------------------------------------------
 void GraphAlgebra::vjp(const Node& n, Algebra& ga, Store& store, const Value& g) {
   // Fused kernels apply when gradients are plain data (Graph1) and fusion is on.
@@ -557,7 +566,8 @@ void GraphAlgebra::vjp(const Node& n, Algebra& ga, Store& store, const Value& g)
           auto it = store.values.find(v1.id);
           ArrayRef cur;
           if (it != store.values.end()) cur = std::move(it->second.data);
-          store.values[v1.id] = Value(ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr));
+          ArrayRef sunk = cur ? ArrayRef() : try_gemm_sink(v1.id, lhs.data, rhs.data, pl, pr);
+          store.values[v1.id] = Value(sunk ? sunk : ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr));
         } else {
           Value l = fix1 ? ga.link(lhs) : lhs, r = fix1 ? rhs : ga.link(rhs);
           Value grad = ga.matmul(l, r, pl, pr);
@@ -572,7 +582,8 @@ void GraphAlgebra::vjp(const Node& n, Algebra& ga, Store& store, const Value& g)
           auto it = store.values.find(v2.id);
           ArrayRef cur;
           if (it != store.values.end()) cur = std::move(it->second.data);
-          store.values[v2.id] = Value(ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr));
+          ArrayRef sunk = cur ? ArrayRef() : try_gemm_sink(v2.id, lhs.data, rhs.data, pl, pr);
+          store.values[v2.id] = Value(sunk ? sunk : ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr));
         } else {
           Value l = fix2 ? lhs : ga.link(lhs), r = fix2 ? ga.link(rhs) : rhs;
           Value grad = ga.matmul(l, r, pl, pr);
@@ -627,7 +638,9 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
   heap.push(gid);
   Id guard = gid.next_id();
   // final-gradient hook: how many nodes still have to run before a variable's gradient is complete
-  std::vector<uint32_t> waiting;  // by node index; only variables are counted
+  std::vector<uint32_t>& waiting = waiting_;  // by node index; only variables are counted
+  waiting.clear();
+  served_.clear();
   auto distinct_variable_inputs = [&](const Node& nd, std::vector<uint32_t>& out) {
     out.clear();
     for (auto& in : nd.inputs) {
@@ -646,7 +659,9 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
       for (uint32_t v : scratch) waiting[v]++;
     }
   }
-  std::vector<char> fired(waiting.size(), 0);
+  std::vector<char> fired(waiting.size(), 0), was_variable(waiting.size(), 0);  // (a consuming sweep resets the nodes it passes)
+  for (size_t i = 1; i < was_variable.size(); i++) was_variable[i] = nodes_[i - 1].op == Op::VARIABLE && !nodes_[i - 1].has_update;
+  served_.assign(waiting.size(), 0);
   while (!heap.empty()) {
     Id id = heap.top();
     heap.pop();
@@ -680,7 +695,7 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
       for (uint32_t v : scratch)
         if (--waiting[v] == 0) {
           const Value* gv = store->get(Id{arena_id_, v});
-          if (gv && gv->data) { fired[v] = 1; final_hook_(Id{arena_id_, v}, gv->data); }
+          if (gv && gv->data) { fired[v] = 1; if (!served_[v]) final_hook_(Id{arena_id_, v}, gv->data); }
         }
     }
     for (auto& in : node.inputs)
@@ -690,8 +705,10 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
   if (!waiting.empty())  // variables some unreached node also feeds (or the root itself): complete as far as this sweep goes
     for (auto& kv : store->values) {
       const Id vid = kv.first;
-      if (is_variable(vid) && vid.index < fired.size() && !fired[vid.index] && kv.second.data) final_hook_(vid, kv.second.data);
+      if (vid.arena == arena_id_ && vid.index < fired.size() && was_variable[vid.index] && !fired[vid.index] && !served_[vid.index] && kv.second.data)
+        final_hook_(vid, kv.second.data);
     }
+  waiting_.clear();
   return store;
 }
 

@@ -70,6 +70,15 @@ void launch_dot(gadcu_ctx* ctx, gadcu_dtype dt, const void* a, const void* b, bo
 void launch_transpose(gadcu_ctx* ctx, gadcu_dtype dt, const void* in, void* out, uint64_t rows, uint64_t cols);
 void launch_random(gadcu_ctx* ctx, gadcu_dtype dt, void* out, uint64_t n, uint64_t seed, bool normal, double a, double b);
 
+// Fused GEMM -> reduce-scatter (comm.cu): instead of writing C, the epilogue of output tile t = nt * (M/256) + mt
+// stores it, as a dense 256 x 256 column-major block, into the staging buffer of the rank that owns the tile
+// (t mod nranks) over NVLink peer memory: block index (t / nranks) * nranks + rank. The owner sums the nranks
+// partials in rank order afterwards.
+struct GemmPush {
+  float* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // staging base of every rank
+  uint32_t nranks = 0, rank = 0;
+};
+
 // C[M,N] (+)= op(A) * op(B), column-major; batch over `batch` matrices with element strides (0 = broadcast).
 struct GemmArgs {
   gadcu_dtype dt = GADCU_F32;
@@ -83,9 +92,11 @@ struct GemmArgs {
   bool accumulate = false;    // C = C + A*B (gradient accumulation fused into the epilogue)
   Buffer* a_buf = nullptr;    // owning buffers when an operand is a whole dense buffer (TF32 split cache)
   Buffer* b_buf = nullptr;
+  const GemmPush* push = nullptr;  // tensor-core pair kernel only (M, N multiples of 256)
 };
 void launch_gemm(gadcu_ctx* ctx, const GemmArgs& g);
 bool gemm_tc_supported(const GemmArgs& g);  // tcgen05 3xTF32 path applies
+bool gemm_push_supported(const GemmArgs& g);  // ... and its CTA-pair kernel, which can push tiles to peers
 
 }  // namespace k
 }  // namespace gadcu

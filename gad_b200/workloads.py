@@ -74,25 +74,22 @@ def mlp_forward(g, X: CuArray, Ws: Sequence[CuArray], bs: Sequence[CuArray], tar
 
 
 def mlp_step(ctx: Context, X: CuArray, Ws: Sequence[CuArray], bs: Sequence[CuArray], target: CuArray,
-             comm: Optional[Comm] = None, overlap: bool = False) -> Tuple[CuArray, List[CuArray], List[CuArray]]:
+             comm: Optional[Comm] = None, overlap: bool = True) -> Tuple[CuArray, List[CuArray], List[CuArray]]:
     """One forward + backward over this rank's rows of the batch; with `comm`, the weight gradients
     and the loss are summed over ranks (the reference sums per-example gradients: net_ext.rs:62-65).
-    With `overlap` each gradient's all-reduce starts as soon as the sweep has completed it (the last layer's while
-    the layers below are still being differentiated); otherwise one grouped all-reduce after the sweep. Measured on
-    2x B200 the overlapped form is SLOWER (NCCL's CTAs and the persistent one-CTA-per-SM GEMM fight for SMs: 147 vs
-    189 steps/s), so it is off by default.
+    With `overlap` the sweep is the data-parallel one (gadcu_evaluate_gradients_dp): the dW GEMMs reduce-scatter
+    their tiles over NVLink peer memory from the epilogue and the gather runs on the communicator's stream while the
+    layers below are still being differentiated; otherwise one grouped NCCL all-reduce after the sweep.
     Returns (loss scalar, dL/dW_l, dL/db_l) as device arrays; nothing is read back to the host."""
     g = Graph1(ctx)
     loss, vW, vb = mlp_forward(g, X, Ws, bs, target)
     lossd = loss.data()
     dp = comm is not None and comm.nranks > 1
-    if dp and overlap:
-        comm.allreduce_sum_async([lossd])  # travels during the sweep; joined by it
     store = g.evaluate_gradients_once(loss.gid(), 1.0, comm if overlap else None)
     gW = [store.get(v.gid()) for v in vW]
     gb = [store.get(v.gid()) for v in vb]
-    if dp and not overlap:
-        comm.allreduce_sum(gW + gb + [lossd])
+    if dp:
+        comm.allreduce_sum([lossd] if overlap else gW + gb + [lossd])
     return lossd, gW, gb
 
 
