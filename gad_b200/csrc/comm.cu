@@ -205,6 +205,22 @@ __global__ void __launch_bounds__(256) dp_reduce_publish_kernel(const float4* __
   }
 }
 
+// Alternative to the tile-pushing GEMM epilogue (GADCU_DP_PUSH=kernel): the GEMM writes its partial product locally at
+// full speed and this kernel, on the communicator's stream, scatters the tiles to their owners' staging buffers.
+struct PeerStaging { float* p[8]; };
+__global__ void __launch_bounds__(256) dp_scatter_kernel(const float* __restrict__ partial, PeerStaging staging, uint32_t M, uint32_t num_mt,
+                                                         uint32_t tiles, uint32_t nranks, uint32_t rank) {
+  const uint64_t total = uint64_t(tiles) * 16384u;  // float4s
+  for (uint64_t i = uint64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += uint64_t(gridDim.x) * 256) {
+    const uint32_t t = uint32_t(i >> 14), v = uint32_t(i & 16383u);
+    const uint32_t mt = t % num_mt, nt = t / num_mt;
+    const uint32_t row = (v * 4u) & 255u, col = (v * 4u) >> 8;
+    const float4 x = __ldcs(reinterpret_cast<const float4*>(partial + uint64_t(nt * 256u + col) * M + mt * 256u + row));
+    float* dst = staging.p[t % nranks] + (uint64_t(t / nranks) * nranks + rank) * 65536u + v * 4u;
+    *reinterpret_cast<float4*>(dst) = x;
+  }
+}
+
 void ensure_heap(gadcu_comm* comm, size_t bytes) {
   if (comm->heap.slot_bytes >= bytes) return;
   if (comm->heap.local) {  // sized by the first gradient that came through; a larger one later goes through NCCL
@@ -382,11 +398,17 @@ ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, M
   push.nranks = uint32_t(comm->nranks);
   push.rank = uint32_t(comm->rank);
   for (int r = 0; r < comm->nranks; r++) push.peer[r] = comm->heap.staging(r, slot);
-  g.push = &push;
+  // GADCU_DP_PUSH = epilogue (default): the GEMM's epilogue stores each tile into its owner's staging buffer;
+  //               = kernel: plain GEMM, then a scatter kernel on the communicator's stream
+  static const bool push_from_epilogue = [] {
+    const char* e = getenv("GADCU_DP_PUSH");
+    return !(e && std::string(e) == "kernel");
+  }();
   ArrayRef out = new_array(ctx, GADCU_F32, rd);
   g.C = out->ptr();
+  if (push_from_epilogue) g.push = &push;
   mark(comm, "compute: gemm start", ctx->stream);
-  k::launch_gemm(ctx, g);  // compute stream: partial tiles land in their owners' staging buffers
+  k::launch_gemm(ctx, g);  // compute stream; with the pushing epilogue the partial tiles land in their owners' staging buffers
   mark(comm, "compute: gemm end", ctx->stream);
   cudaEvent_t ev;
   GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -396,9 +418,18 @@ ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, M
   // communicator stream, overlapping the rest of the sweep: all partials have arrived -> reduce + publish -> all
   // results have arrived -> copy out
   mark(comm, "comm: after gemm", comm->stream);
+  const uint32_t num_mt = uint32_t(g.M / 256), tiles = num_mt * uint32_t(g.N / 256);
+  if (!push_from_epilogue) {
+    PeerStaging st;
+    for (int r = 0; r < 8; r++) st.p[r] = push.peer[r];
+    const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(tiles) * 64, uint64_t(ctx->sm_count) * 4));
+    dp_scatter_kernel<<<grid, 256, 0, comm->stream>>>(static_cast<const float*>(out->ptr()), st, uint32_t(g.M), num_mt, tiles,
+                                                      uint32_t(comm->nranks), uint32_t(comm->rank));
+    ctx->count_launch();
+    mark(comm, "comm: scattered", comm->stream);
+  }
   barrier_on(comm, comm->stream);
   mark(comm, "comm: barrier 1 done", comm->stream);
-  const uint32_t num_mt = uint32_t(g.M / 256), tiles = num_mt * uint32_t(g.N / 256);
   PeerResults res;
   for (int r = 0; r < 8; r++) res.p[r] = r < comm->nranks ? comm->heap.result(r, slot) : nullptr;
   const uint32_t owned = tiles > uint32_t(comm->rank) ? (tiles - comm->rank + comm->nranks - 1) / comm->nranks : 0;
