@@ -285,7 +285,7 @@ class GradientId:
         self.arena, self.index = arena, index
 
     def __eq__(self, other):
-        return (self.arena, self.index) == (other.arena, other.index)
+        return isinstance(other, GradientId) and (self.arena, self.index) == (other.arena, other.index)
 
     def __hash__(self):
         return hash((self.arena, self.index))

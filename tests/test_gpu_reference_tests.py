@@ -16,31 +16,7 @@ with open(os.path.join(ROOT, "tests", "golden", "reference_known_answers.json"))
     GOLDEN = json.load(f)
 
 
-def estimate_gradient(ctx, x, direction, eps, f):
-    """gad/src/arrayfire.rs:120-150: central differences of dot(f(x), direction)."""
-    ev = gb.Eval(ctx)
-    v = x.astype(np.float32).copy()
-    grad = np.zeros_like(v)
-    d = ev.constant(direction)
-    flat, gflat = v.reshape(-1, order="F"), grad.reshape(-1, order="F")
-    for i in range(flat.size):
-        x0 = flat[i]
-        flat[i] = x0 + eps
-        # the dot with the direction is taken in f64 on the host so that the difference quotient is
-        # limited by the f32 rounding of f itself, as in the reference's CPU runs
-        dh = np.asarray(direction, dtype=np.float64).reshape(-1, order="F")
-        y2 = float(np.dot(to_np(f(ev, ev.constant(flat.reshape(v.shape, order="F")))).reshape(-1, order="F").astype(np.float64), dh))
-        flat[i] = x0 - eps
-        y1 = float(np.dot(to_np(f(ev, ev.constant(flat.reshape(v.shape, order="F")))).reshape(-1, order="F").astype(np.float64), dh))
-        gflat[i] = (y2 - y1) / (eps + eps)
-        flat[i] = x0
-    return gflat.reshape(v.shape, order="F")
-
-
-def almost_all_equal(a, b, precision):  # arrayfire.rs:153-163 (L-infinity)
-    a, b = np.squeeze(a), np.squeeze(b)
-    assert a.shape == b.shape
-    assert np.max(np.abs(a - b)) < precision
+from gad_b200.testing import assert_almost_all_equal as almost_all_equal, estimate_gradient  # arrayfire.rs:114-164
 
 
 @pytest.mark.parametrize("case", GOLDEN["scalar_f32_direction_1p7"], ids=lambda c: c["name"])
