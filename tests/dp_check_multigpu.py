@@ -1,6 +1,7 @@
 """Multi-GPU check of the data-parallel sweep (not collected by pytest: needs >= 2 GPUs):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/dp_check_multigpu.py
-the fused peer-memory exchange == the grouped NCCL all-reduce (bit for bit at 2 ranks) == the single-GPU full batch to 1e-5."""
+the fused peer-memory exchange == the grouped NCCL all-reduce (bit for bit at 2 ranks, to 1e-5 beyond) == the
+single-GPU full batch to a few 1e-5; a second fused step reproduces the first exactly (deterministic order)."""
 import os, sys, numpy as np
 os.environ["NCCL_DEBUG"] = "WARN"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -29,7 +30,12 @@ c = run(True)
 assert c[0] == a[0] and all(np.array_equal(x, y) for x, y in zip(a[1] + a[2], c[1] + c[2])), "second fused step differs"
 full = wl.mlp_step(ctx, ctx.array(X), [ctx.array(w) for w in Ws], [ctx.array(b) for b in bs], ctx.array(T))
 fl, fW = full[0].item(), [g.numpy() for g in full[1]]
-ok = a[0] == b[0] and all(np.array_equal(x, y) for x, y in zip(a[1] + a[2], b[1] + b[2]))
+# 2 ranks: a + b is the same in any order, so the two paths agree bit for bit; more ranks: the fused path adds the
+# partials in rank order, NCCL in ring / tree order -> equal to f32 rounding of the sum
+exact = a[0] == b[0] and all(np.array_equal(x, y) for x, y in zip(a[1] + a[2], b[1] + b[2]))
+close = max(float(np.abs(x - y).max() / np.abs(y).max()) for x, y in zip(a[1] + a[2], b[1] + b[2]))
+assert (exact if world == 2 else close <= 1e-5), (exact, close)
+ok = f"exact={exact} max_rel={close:.1e}"
 rel = max(float(np.abs(x - y).max() / np.abs(y).max()) for x, y in zip(a[1], fW))
 print(f"rank {rank}: overlap == grouped: {ok}; loss {a[0]} vs full-batch {fl}; max rel diff of dW vs single-GPU full batch {rel:.2e}", flush=True)
 dist.destroy_process_group()
