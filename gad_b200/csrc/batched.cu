@@ -446,7 +446,7 @@ struct JitPlan {
   std::vector<int32_t> sched;
 };
 
-const JitPlan* g_plan = nullptr;  // set while a plan is being rendered (single-threaded under the program's mutex)
+thread_local const JitPlan* g_plan = nullptr;  // the plan being rendered by this thread
 std::string reg_name(int32_t r) { return "r" + std::to_string(g_plan->local.at(r)); }
 
 std::string gen_source(const SymProgram& P, const JitPlan& J, const std::unordered_map<int32_t, int>& imm_slot) {
