@@ -7,7 +7,9 @@
 namespace gadcu {
 namespace k {
 
-void launch_gemm_tc(gadcu_ctx* ctx, const GemmArgs& g);  // gemm_tc.cu
+void launch_gemm_tc(gadcu_ctx* ctx, const GemmArgs& g);    // gemm_tc.cu
+void launch_gemm_dmma(gadcu_ctx* ctx, const GemmArgs& g);  // gemm_dmma.cu
+bool gemm_dmma_supported(const GemmArgs& g);
 
 namespace {
 
@@ -87,6 +89,11 @@ void launch_gemm(gadcu_ctx* ctx, const GemmArgs& g) {
   if (g.M * g.N * g.batch == 0) return;
   if (gemm_tc_supported(g)) {
     launch_gemm_tc(ctx, g);
+    return;
+  }
+  if (g.push) fail(GADCU_ERR_UNSUPPORTED, "gemm: the tile-pushing epilogue exists on the f32 tensor-core path only");
+  if (gemm_dmma_supported(g)) {
+    launch_gemm_dmma(ctx, g);
     return;
   }
   dim3 grid(unsigned((g.M + BM - 1) / BM), unsigned((g.N + BN - 1) / BN), unsigned(g.batch));
