@@ -345,6 +345,15 @@ class Store:
         self.ctx.lib.gadcu_store_ids(self.handle, buf, n)
         return list(buf[:n])
 
+    def rerun(self, columns: Sequence["CuArray"]) -> list:
+        """Batched tapes only: the same tapes at new points (one column per variable, creation order) through the
+        already compiled lane program; returns the variables' gradient columns."""
+        n = len(columns)
+        arr = (C.c_void_p * n)(*[c.handle for c in columns])
+        out = (C.c_void_p * n)()
+        _check(self.ctx.lib.gadcu_batched_rerun(self.handle, arr, n, out))
+        return [CuArray(self.ctx, C.c_void_p(h)) if h else None for h in out]
+
     def program_stats(self) -> dict:
         a, b = C.c_uint64(), C.c_uint64()
         _check(self.ctx.lib.gadcu_batched_program_stats(self.handle, C.byref(a), C.byref(b)))

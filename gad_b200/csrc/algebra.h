@@ -255,8 +255,10 @@ struct gadcu_store {
   // fused: contribution = op(ins...) computed and accumulated by one kernel (Graph1 + fusion only)
   void add_fused(gadcu::EvalAlgebra& ev, gadcu::Id id, gadcu::k::EwOp op, std::initializer_list<const gadcu::ArrayRef*> ins,
                  double c = 0.0, double c2 = 0.0);
-  // batched-tape stats
+  // batched-tape stats, and what gadcu_batched_rerun needs (batched.cu)
   uint64_t program_instructions = 0, program_slots = 0;
+  std::shared_ptr<void> lane_program;
+  std::vector<int32_t> lane_gradient_regs;
 };
 
 namespace gadcu {
@@ -273,6 +275,7 @@ class GraphAlgebra final : public Algebra {
   size_t num_nodes() const override { return nodes_.size(); }
   Algebra& eval() { return *eval_; }
   void set_kind(gadcu_algebra_kind k) { kind_override_ = k; }
+  const std::vector<ArrayRef>& variable_data() const { return variable_data_; }
   bool is_variable(Id id) const { return id.arena == arena_id_ && id.index >= 1 && id.index <= nodes_.size() && nodes_[id.index - 1].op == Op::VARIABLE && !nodes_[id.index - 1].has_update; }
 
   Value variable(ArrayRef data) override;
@@ -346,6 +349,7 @@ class GraphAlgebra final : public Algebra {
   uint32_t arena_id_;
   std::shared_ptr<Algebra> eval_;
   std::vector<Node> nodes_;
+  std::vector<ArrayRef> variable_data_;  // batched tapes: the column of every variable, in creation order
 };
 
 }  // namespace gadcu

@@ -72,6 +72,19 @@ struct SymProgram {
   std::map<std::tuple<const void*, int, uint64_t>, int32_t> input_reg;  // dedupe loads by (buffer, kind, d0)
   std::unordered_map<int32_t, ArrayRef> cache;       // register -> materialised column
   std::vector<int32_t> live;                         // handles alive per register
+  std::vector<int32_t> variable_inputs;              // batched tapes: input index of every variable, in creation order
+  // batched tapes: what a finished plan needs to run again for the same outputs (planned with no column cached), so a
+  // re-run at new points costs a parameter block and a launch, not a re-plan of a thousand instructions
+  struct Compiled {
+    const jit::Kernel* kernel = nullptr;
+    std::vector<int32_t> in_inputs;  // parameter slot -> index into `inputs`
+    std::vector<uint64_t> tile_d0;
+    std::vector<double> imms;
+    int V = 1, U = 1, block = 128;
+    uint64_t instructions = 0, values = 0;
+  };
+  std::map<std::vector<int32_t>, Compiled> compiled;
+  std::vector<ArrayRef> launch_compiled(const Compiled& c, size_t nout);
   std::map<std::tuple<uint16_t, int32_t, int32_t, int32_t, int32_t, double>, int32_t> value_number;  // array mode: CSE
   uint64_t last_instructions = 0, last_slots = 0;
   std::mutex mu;
@@ -436,6 +449,7 @@ struct JitPlan {
   std::vector<int32_t> outs;
   std::vector<double> imms;
   std::vector<const void*> in_ptrs;
+  std::vector<int32_t> in_inputs;              // per parameter slot: index into the program's inputs (-1: a cached column)
   std::vector<uint64_t> tile_d0;               // one per col/row input, in (col..., row...) order
   std::unordered_map<int32_t, int32_t> local;  // program register -> dense numbering of the needed ones, so that the
                                                // same structure at different positions of a program is the same kernel
@@ -602,8 +616,39 @@ std::string gen_source(const SymProgram& P, const JitPlan& J, const std::unorder
 
 }  // namespace
 
+std::vector<ArrayRef> SymProgram::launch_compiled(const Compiled& c, size_t nout) {
+  // outputs + parameter block (layout of `struct P`: every field is 8 bytes wide)
+  std::vector<ArrayRef> out_cols;
+  for (size_t j = 0; j < nout; j++) out_cols.push_back(new_array(ctx, dtype, Dim4(lanes)));
+  const size_t NI = std::max<size_t>(c.in_inputs.size(), 1), NO = std::max<size_t>(nout, 1), NT = std::max<size_t>(c.tile_d0.size(), 1),
+               NM = std::max<size_t>(c.imms.size(), 1);
+  std::vector<uint64_t> params(NI + NO + 1 + NT + NM, 0);
+  for (size_t i = 0; i < c.in_inputs.size(); i++) params[i] = reinterpret_cast<uint64_t>(inputs[size_t(c.in_inputs[i])]->ptr());
+  for (size_t i = 0; i < out_cols.size(); i++) params[NI + i] = reinterpret_cast<uint64_t>(out_cols[i]->ptr());
+  params[NI + NO] = lanes;
+  for (size_t i = 0; i < c.tile_d0.size(); i++) params[NI + NO + 1 + i] = c.tile_d0[i];
+  for (size_t i = 0; i < c.imms.size(); i++) std::memcpy(&params[NI + NO + 1 + NT + i], &c.imms[i], 8);
+  const uint64_t per_block = uint64_t(c.block) * uint64_t(c.V) * uint64_t(c.U);
+  uint64_t grid = (lanes + per_block - 1) / per_block;
+  const uint64_t cap = uint64_t(ctx->sm_count) * (c.block == 256 ? 8 : 16);
+  if (grid > cap && c.V > 1) grid = cap;
+  if (grid > 0x7fffffffull) grid = 0x7fffffffull;
+  if (grid == 0) grid = 1;
+  ProfileScope prof_scope(ctx, array_mode ? PROF_EW : PROF_OTHER);
+  void* args[] = {params.data()};
+  jit::launch(ctx, c.kernel, unsigned(grid), unsigned(c.block), args);
+  last_instructions = c.instructions;
+  last_slots = c.values;
+  return out_cols;
+}
+
 std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   const int32_t n = int32_t(instrs.size());
+  const bool reusable = !array_mode && cache.empty();
+  if (reusable) {
+    auto it = compiled.find(todo);
+    if (it != compiled.end()) return launch_compiled(it->second, todo.size());
+  }
   auto is_load = [](uint16_t op) { return op == S_LOAD || op == S_LOADU || op == S_LOADCOL || op == S_LOADROW; };
   // 1. what the requested outputs depend on; a register that already has a materialised column is a leaf
   std::vector<char> needed(n, 0);
@@ -629,18 +674,23 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
     if (cached != cache.end()) {
       J.dense.push_back({r, int(J.in_ptrs.size())});
       J.in_ptrs.push_back(cached->second->ptr());
+      J.in_inputs.push_back(-1);
     } else if (I.op == S_LOAD) {
       J.dense.push_back({r, int(J.in_ptrs.size())});
       J.in_ptrs.push_back(inputs[I.a]->ptr());
+      J.in_inputs.push_back(I.a);
     } else if (I.op == S_LOADU) {
       J.uniform.push_back({r, int(J.in_ptrs.size())});
       J.in_ptrs.push_back(inputs[I.a]->ptr());
+      J.in_inputs.push_back(I.a);
     } else if (I.op == S_LOADCOL) {
       J.col.push_back({r, int(J.in_ptrs.size())});
       J.in_ptrs.push_back(inputs[I.a]->ptr());
+      J.in_inputs.push_back(I.a);
     } else if (I.op == S_LOADROW) {
       J.row.push_back({r, int(J.in_ptrs.size())});
       J.in_ptrs.push_back(inputs[I.a]->ptr());
+      J.in_inputs.push_back(I.a);
     } else {
       J.order.push_back(r);
       if (I.op == S_CONST || I.op == S_ADDC || I.op == S_MULC || I.op == S_POWI || I.op == S_POWF) {
@@ -812,6 +862,17 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
       if (f) { fprintf(f, "// ---- key %zu bytes, %zu instructions\n%s\n", key.size(), J.order.size(), src.c_str()); fclose(f); }
     }
     kernel = jit::compile(key, src, "lane_program");
+  }
+  if (reusable && J.imms.size() * 8 + (J.in_ptrs.size() + J.outs.size() + J.tile_d0.size() + 1) * 8 <= 4000) {
+    Compiled c;
+    c.kernel = kernel;
+    c.in_inputs = J.in_inputs;
+    c.tile_d0 = J.tile_d0;
+    c.imms = J.imms;
+    c.V = J.V; c.U = J.U; c.block = J.block;
+    c.instructions = last_instructions;
+    c.values = last_slots;
+    compiled[todo] = std::move(c);
   }
   // 4. outputs + parameter block (layout of `struct P`: every field is 8 bytes wide)
   std::vector<ArrayRef> out_cols;
@@ -1181,7 +1242,59 @@ std::unique_ptr<Store> batched_evaluate_gradients(GraphAlgebra& g, Id id, ArrayR
   }
   store->program_instructions = sym->program()->last_instructions;
   store->program_slots = sym->program()->last_slots;
+  // what a re-run needs: the program and, per variable (creation order), the register of its gradient
+  store->lane_program = sym->program();
+  {
+    // input slot of every variable (creation order): variables are loaded by buffer on first use
+    auto prog = sym->program();
+    std::lock_guard<std::mutex> lk(prog->mu);
+    prog->variable_inputs.clear();
+    for (const ArrayRef& data : g.variable_data()) {
+      int32_t slot = -1;
+      if (data && data->buf) {
+        for (int kind = 0; kind < 2 && slot < 0; kind++) {
+          auto it = prog->input_reg.find(std::make_tuple(static_cast<const void*>(data->ptr()), kind, uint64_t(0)));
+          if (it != prog->input_reg.end()) slot = prog->instrs[it->second].a;  // (a load's operand is its input index)
+        }
+      }
+      prog->variable_inputs.push_back(slot);  // -1: the tape never read this variable
+    }
+  }
+  for (Id vid : var_ids) {
+    auto it = std::find(ids.begin(), ids.end(), vid);
+    store->lane_gradient_regs.push_back(it == ids.end() ? -1 : regs[size_t(it - ids.begin())]);
+  }
   return store;
+}
+
+// The same tapes at new points: swap the variables' columns, run the compiled program again (one kernel launch, no
+// re-recording). Returns the gradient column of every variable (null where the sweep left none).
+std::vector<ArrayRef> batched_rerun(Store& store, const std::vector<ArrayRef>& columns) {
+  auto prog = std::static_pointer_cast<SymProgram>(store.lane_program);
+  if (!prog) fail(GADCU_ERR_INVALID, "rerun: the store does not come from a batched sweep");
+  if (columns.size() != prog->variable_inputs.size())
+    fail(GADCU_ERR_LENGTHS, "rerun: expected one column per variable (" + std::to_string(prog->variable_inputs.size()) + "), got " +
+                                std::to_string(columns.size()));
+  std::vector<int32_t> regs;
+  {
+    std::lock_guard<std::mutex> lk(prog->mu);
+    for (size_t i = 0; i < columns.size(); i++) {
+      ArrayRef c = materialize(columns[i]);
+      if (c->dtype != prog->dtype) fail(GADCU_ERR_TYPE, "rerun: dtype mismatch");
+      if (c->elements() != prog->lanes) fail(GADCU_ERR_DIMENSIONS, "rerun: expected a [lanes] column, got " + c->dims.str());
+      if (prog->variable_inputs[i] >= 0) prog->inputs[size_t(prog->variable_inputs[i])] = c;
+    }
+    prog->cache.clear();  // every computed column belonged to the old points
+    for (int32_t r : store.lane_gradient_regs)
+      if (r >= 0) regs.push_back(r);
+  }
+  std::vector<ArrayRef> cols = prog->run(regs);
+  std::vector<ArrayRef> out(store.lane_gradient_regs.size());
+  size_t j = 0;
+  for (size_t i = 0; i < out.size(); i++)
+    if (store.lane_gradient_regs[i] >= 0) out[i] = cols[j++];
+  store.program_instructions = prog->last_instructions;
+  return out;
 }
 
 }  // namespace gadcu
@@ -1201,6 +1314,14 @@ gadcu_status gadcu_batched_force(gadcu_algebra* g, const gadcu_value* v, gadcu_a
     (void)g;
     ArrayRef a(v->data, true);
     *out = materialize(a).detach();
+  });
+}
+gadcu_status gadcu_batched_rerun(gadcu_store* s, gadcu_array* const* columns, size_t n, gadcu_array** gradients_out) {
+  return guard([&] {
+    std::vector<ArrayRef> cols;
+    for (size_t i = 0; i < n; i++) cols.emplace_back(columns[i], true);
+    std::vector<ArrayRef> grads = batched_rerun(*s, cols);
+    for (size_t i = 0; i < grads.size(); i++) gradients_out[i] = grads[i] ? grads[i].detach() : nullptr;
   });
 }
 gadcu_status gadcu_batched_program_stats(const gadcu_store* s, uint64_t* instructions, uint64_t* slots) {

@@ -10,6 +10,7 @@ std::unique_ptr<GraphAlgebra> make_batched(gadcu_ctx* ctx, gadcu_dtype dt, uint6
 // Graph1::evaluate_gradients over lanes: symbolic sweep, then one kernel computes the gradients of
 // all variables. Other store entries stay symbolic and are computed when read.
 std::unique_ptr<Store> batched_evaluate_gradients(GraphAlgebra& g, Id id, ArrayRef seed, bool once);
+std::vector<ArrayRef> batched_rerun(Store& store, const std::vector<ArrayRef>& columns);
 
 
 // ---- deferred elementwise regions of array tapes (batched.cu) ---------------------------------------

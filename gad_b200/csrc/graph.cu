@@ -48,6 +48,7 @@ GraphAlgebra::GraphAlgebra(gadcu_ctx* c, bool higher_order, std::shared_ptr<Alge
 
 // graph.rs:94-101
 Value GraphAlgebra::variable(ArrayRef data) {
+  if (kind_override_ == GADCU_BATCHED1) variable_data_.push_back(data);  // gadcu_batched_rerun swaps these columns
   nodes_.emplace_back();
   return Value(std::move(data), Id{arena_id_, uint32_t(nodes_.size())});
 }

@@ -251,6 +251,10 @@ GADCU_API gadcu_status gadcu_capture_destroy(gadcu_capture* c);
  * into one per-lane program and runs it with one lane per thread. */
 GADCU_API gadcu_status gadcu_batched_create(gadcu_ctx* ctx, gadcu_dtype dt, uint64_t lanes, gadcu_algebra** out);
 GADCU_API gadcu_status gadcu_batched_force(gadcu_algebra* g, const gadcu_value* v, gadcu_array** out); /* forward value column */
+/* The same tapes at new points: `columns[i]` replaces the data of the i-th variable (creation order); the compiled
+ * lane program runs again — one kernel launch, nothing is re-recorded — and gradients_out[i] receives the gradient
+ * column of the i-th variable (+1 reference; NULL where the sweep produced none). `s` must come from a batched sweep. */
+GADCU_API gadcu_status gadcu_batched_rerun(gadcu_store* s, gadcu_array* const* columns, size_t n, gadcu_array** gradients_out);
 GADCU_API gadcu_status gadcu_batched_program_stats(const gadcu_store* s, uint64_t* instructions, uint64_t* slots);
 
 /* ---- data parallelism over the batch dimension (new: the reference is single-process) ------------

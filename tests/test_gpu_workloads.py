@@ -35,6 +35,27 @@ def test_batched_rosenbrock_matches_scalar_tape_bit_for_bit(ctx, oracle, n, lane
     assert len(store.ids()) == g.num_nodes()
 
 
+def test_batched_rerun_at_new_points_equals_a_fresh_tape(ctx, oracle):
+    """gadcu_batched_rerun: the compiled lane program at new columns == recording the tapes again == the scalar tape."""
+    n, lanes = 16, 777
+    rng = np.random.default_rng(7)
+    x0, x1 = -1.2 + 2.4 * rng.random((n, lanes)), -1.2 + 2.4 * rng.random((n, lanes))
+    g, f, grads, store = wl.rosenbrock_batched_gradients(ctx, [ctx.array(x0[i]) for i in range(n)])
+    launches = ctx.launches()
+    again = store.rerun([ctx.array(x1[i]) for i in range(n)])
+    assert ctx.launches() - launches == 1  # one kernel, nothing re-recorded
+    got = np.stack([to_np(c)[:, 0, 0, 0] for c in again])
+    _, _, fresh, _ = wl.rosenbrock_batched_gradients(ctx, [ctx.array(x1[i]) for i in range(n)])
+    assert np.array_equal(got, np.stack([to_np(c)[:, 0, 0, 0] for c in fresh]))
+    _, ograd, _ = oracle.rosenbrock_batch(x1, nthreads=4)
+    assert np.array_equal(got, ograd)
+    # the first sweep's results are untouched
+    _, ograd0, _ = oracle.rosenbrock_batch(x0, nthreads=4)
+    assert np.array_equal(np.stack([to_np(c)[:, 0, 0, 0] for c in grads]), ograd0)
+    with pytest.raises(gb.LengthsError):
+        store.rerun([ctx.array(x1[0])])
+
+
 def test_batched_tape_golden_point_and_f32(ctx):
     cols = [ctx.array(np.array([-1.2, 1.0])), ctx.array(np.array([1.0, 1.0]))]
     g, f, grads, _ = wl.rosenbrock_batched_gradients(ctx, cols)
