@@ -330,7 +330,7 @@ class GraphAlgebra final : public Algebra {
   // gradient: may compute it itself (the data-parallel GEMM whose epilogue reduce-scatters over NVLink) and return
   // the array that will hold the rank-summed gradient, or return null to decline. The final hook is not called for
   // a variable served this way.
-  using GemmSink = std::function<ArrayRef(Id, const ArrayRef& lhs, const ArrayRef& rhs, MatProp pl, MatProp pr)>;
+  using GemmSink = std::function<ArrayRef(Id, const ArrayRef& lhs, const ArrayRef& rhs, MatProp pl, MatProp pr, bool last)>;  // last: no other large variable is still waiting for its gradient
   void set_gemm_sink(GemmSink h) { gemm_sink_ = std::move(h); }
   std::unique_ptr<Store> evaluate_gradients(Id id, ArrayRef seed, bool once);
   std::unique_ptr<Store> compute_gradients(Id id, const Value& seed);

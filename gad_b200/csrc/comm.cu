@@ -357,7 +357,7 @@ bool small_allreduce(gadcu_comm* comm, gadcu_array* const* arrays, size_t n) {
 
 // The matmul VJP's product IS a variable's gradient: compute it with the tile-pushing epilogue and run the rest of
 // the exchange on the communicator's stream. Returns the array that holds the rank-summed gradient after the join.
-ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, MatProp p1, MatProp p2) {
+ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, MatProp p1, MatProp p2, bool last) {
   gadcu_ctx* ctx = comm->ctx;
   if (a_in->dtype != GADCU_F32 || b_in->dtype != GADCU_F32) return ArrayRef();
   const Dim4 rd = check::matmul(a_in->dims, b_in->dims, p1, p2);
@@ -389,62 +389,77 @@ ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, M
     comm->no_peer_memory = true;
     return ArrayRef();
   }
-  const int slot = int(comm->exchanges % kSlots);
-  // the slot's previous exchange (three exchanges ago) must have been copied out here before anyone may push into it
-  // again: peers push only after passing a barrier that this rank enters after this wait
-  if (comm->exchanges >= uint64_t(kSlots)) GADCU_CUDA(cudaStreamWaitEvent(ctx->stream, comm->slot_done[slot], 0));
-  comm->exchanges++;
-  k::GemmPush push;
-  push.nranks = uint32_t(comm->nranks);
-  push.rank = uint32_t(comm->rank);
-  for (int r = 0; r < comm->nranks; r++) push.peer[r] = comm->heap.staging(r, slot);
   // GADCU_DP_PUSH = epilogue (default): the GEMM's epilogue stores each tile into its owner's staging buffer;
   //               = kernel: plain GEMM, then a scatter kernel on the communicator's stream
   static const bool push_from_epilogue = [] {
     const char* e = getenv("GADCU_DP_PUSH");
     return !(e && std::string(e) == "kernel");
   }();
+  // The exchange of the sweep's LAST gradient has nothing left to hide behind: it is cut into column chunks so that
+  // the gather of one chunk overlaps the GEMM of the next and only the last chunk's gather is exposed.
+  static const uint64_t max_chunks = [] { const char* e = getenv("GADCU_DP_TAIL_CHUNKS"); return e ? uint64_t(std::max(1, atoi(e))) : uint64_t(1); }();  // measured on 8 GPUs: 2 chunks = no gain, 4 = slower (barrier latency dominates)
+  uint64_t chunks = 1;
+  if (last && !g.tb)
+    while (chunks * 2 <= max_chunks && g.N % (chunks * 2 * 256) == 0) chunks *= 2;
+  const uint64_t Nc = g.N / chunks;
   ArrayRef out = new_array(ctx, GADCU_F32, rd);
-  g.C = out->ptr();
-  if (push_from_epilogue) g.push = &push;
-  mark(comm, "compute: gemm start", ctx->stream);
-  k::launch_gemm(ctx, g);  // compute stream; with the pushing epilogue the partial tiles land in their owners' staging buffers
-  mark(comm, "compute: gemm end", ctx->stream);
-  cudaEvent_t ev;
-  GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  GADCU_CUDA(cudaEventRecord(ev, ctx->stream));
-  GADCU_CUDA(cudaStreamWaitEvent(comm->stream, ev, 0));
-  GADCU_CUDA(cudaEventDestroy(ev));
-  // communicator stream, overlapping the rest of the sweep: all partials have arrived -> reduce + publish -> all
-  // results have arrived -> copy out
-  mark(comm, "comm: after gemm", comm->stream);
-  const uint32_t num_mt = uint32_t(g.M / 256), tiles = num_mt * uint32_t(g.N / 256);
-  if (!push_from_epilogue) {
-    PeerStaging st;
-    for (int r = 0; r < 8; r++) st.p[r] = push.peer[r];
-    const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(tiles) * 64, uint64_t(ctx->sm_count) * 4));
-    dp_scatter_kernel<<<grid, 256, 0, comm->stream>>>(static_cast<const float*>(out->ptr()), st, uint32_t(g.M), num_mt, tiles,
-                                                      uint32_t(comm->nranks), uint32_t(comm->rank));
-    ctx->count_launch();
-    mark(comm, "comm: scattered", comm->stream);
+  const float* Bfull = static_cast<const float*>(g.B);
+  for (uint64_t c = 0; c < chunks; c++) {
+    k::GemmArgs gc = g;
+    gc.N = Nc;
+    gc.B = Bfull + c * Nc * g.ldb;                          // columns [c Nc, (c+1) Nc) of the stored [K, N] operand
+    if (chunks > 1) gc.b_buf = nullptr;                     // (a sub-view: its TF32 split is its own)
+    float* out_c = static_cast<float*>(out->ptr()) + c * Nc * g.M;
+    gc.C = out_c;
+    const size_t bytes_c = size_t(g.M) * Nc * 4;
+    const int slot = int(comm->exchanges % kSlots);
+    // the slot's previous exchange (kSlots exchanges ago) must have been copied out here before anyone may push into it
+    // again: peers push only after passing a barrier that this rank enters after this wait
+    if (comm->exchanges >= uint64_t(kSlots)) GADCU_CUDA(cudaStreamWaitEvent(ctx->stream, comm->slot_done[slot], 0));
+    comm->exchanges++;
+    k::GemmPush push;
+    push.nranks = uint32_t(comm->nranks);
+    push.rank = uint32_t(comm->rank);
+    for (int r = 0; r < comm->nranks; r++) push.peer[r] = comm->heap.staging(r, slot);
+    if (push_from_epilogue) gc.push = &push;
+    mark(comm, "compute: gemm start", ctx->stream);
+    k::launch_gemm(ctx, gc);  // compute stream; with the pushing epilogue the partial tiles land in their owners' staging buffers
+    mark(comm, "compute: gemm end", ctx->stream);
+    cudaEvent_t ev;
+    GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    GADCU_CUDA(cudaEventRecord(ev, ctx->stream));
+    GADCU_CUDA(cudaStreamWaitEvent(comm->stream, ev, 0));
+    GADCU_CUDA(cudaEventDestroy(ev));
+    // communicator stream, overlapping the rest of the sweep: all partials have arrived -> reduce + publish -> all
+    // results have arrived -> copy out
+    mark(comm, "comm: after gemm", comm->stream);
+    const uint32_t num_mt = uint32_t(g.M / 256), tiles = num_mt * uint32_t(Nc / 256);
+    if (!push_from_epilogue) {
+      PeerStaging st;
+      for (int r = 0; r < 8; r++) st.p[r] = push.peer[r];
+      const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(tiles) * 64, uint64_t(ctx->sm_count) * 4));
+      dp_scatter_kernel<<<grid, 256, 0, comm->stream>>>(out_c, st, uint32_t(g.M), num_mt, tiles, uint32_t(comm->nranks), uint32_t(comm->rank));
+      ctx->count_launch();
+      mark(comm, "comm: scattered", comm->stream);
+    }
+    barrier_on(comm, comm->stream);
+    mark(comm, "comm: barrier 1 done", comm->stream);
+    PeerResults res;
+    for (int r = 0; r < 8; r++) res.p[r] = r < comm->nranks ? comm->heap.result(r, slot) : nullptr;
+    const uint32_t owned = tiles > uint32_t(comm->rank) ? (tiles - comm->rank + comm->nranks - 1) / comm->nranks : 0;
+    if (owned > 0) {
+      const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(owned) * 64, uint64_t(ctx->sm_count) * 4));
+      dp_reduce_publish_kernel<<<grid, 256, 0, comm->stream>>>(reinterpret_cast<const float4*>(comm->heap.staging(comm->rank, slot)), res,
+                                                               uint32_t(g.M), num_mt, tiles, uint32_t(comm->nranks), uint32_t(comm->rank));
+      ctx->count_launch();
+    }
+    mark(comm, "comm: reduce+publish done", comm->stream);
+    barrier_on(comm, comm->stream);
+    mark(comm, "comm: barrier 2 done", comm->stream);
+    GADCU_CUDA(cudaMemcpyAsync(out_c, comm->heap.result(comm->rank, slot), bytes_c, cudaMemcpyDeviceToDevice, comm->stream));
+    mark(comm, "comm: copy out done", comm->stream);
+    GADCU_CUDA(cudaEventRecord(comm->slot_done[slot], comm->stream));
   }
-  barrier_on(comm, comm->stream);
-  mark(comm, "comm: barrier 1 done", comm->stream);
-  PeerResults res;
-  for (int r = 0; r < 8; r++) res.p[r] = r < comm->nranks ? comm->heap.result(r, slot) : nullptr;
-  const uint32_t owned = tiles > uint32_t(comm->rank) ? (tiles - comm->rank + comm->nranks - 1) / comm->nranks : 0;
-  if (owned > 0) {
-    const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(owned) * 64, uint64_t(ctx->sm_count) * 4));
-    dp_reduce_publish_kernel<<<grid, 256, 0, comm->stream>>>(reinterpret_cast<const float4*>(comm->heap.staging(comm->rank, slot)), res,
-                                                             uint32_t(g.M), num_mt, tiles, uint32_t(comm->nranks), uint32_t(comm->rank));
-    ctx->count_launch();
-  }
-  mark(comm, "comm: reduce+publish done", comm->stream);
-  barrier_on(comm, comm->stream);
-  mark(comm, "comm: barrier 2 done", comm->stream);
-  GADCU_CUDA(cudaMemcpyAsync(out->ptr(), comm->heap.result(comm->rank, slot), bytes, cudaMemcpyDeviceToDevice, comm->stream));
-  mark(comm, "comm: copy out done", comm->stream);
-  GADCU_CUDA(cudaEventRecord(comm->slot_done[slot], comm->stream));
   comm->pending++;
   return out;
 }
@@ -520,7 +535,7 @@ gadcu_status gadcu_evaluate_gradients_dp(gadcu_algebra* g, uint32_t arena, uint3
         graph->set_final_hook([comm](Id, const ArrayRef& grad) { allreduce_async(comm, grad); });
       } else {
         graph->set_final_hook([comm](Id, const ArrayRef& grad) { comm->deferred.push_back(grad); });
-        graph->set_gemm_sink([comm](Id, const ArrayRef& lhs, const ArrayRef& rhs, MatProp pl, MatProp pr) { return dp_gemm(comm, lhs, rhs, pl, pr); });
+        graph->set_gemm_sink([comm](Id, const ArrayRef& lhs, const ArrayRef& rhs, MatProp pl, MatProp pr, bool last) { return dp_gemm(comm, lhs, rhs, pl, pr, last); });
       }
     }
     auto finish = [&] {

@@ -50,6 +50,7 @@ GraphAlgebra::GraphAlgebra(gadcu_ctx* c, bool higher_order, std::shared_ptr<Alge
 Value GraphAlgebra::variable(ArrayRef data) {
   if (kind_override_ == GADCU_BATCHED1) variable_data_.push_back(data);  // gadcu_batched_rerun swaps these columns
   nodes_.emplace_back();
+  if (data) nodes_.back().fwd_dims = data->dims;
   return Value(std::move(data), Id{arena_id_, uint32_t(nodes_.size())});
 }
 
@@ -244,7 +245,11 @@ Value GraphAlgebra::softmax_as(const Value& v, const Dim4& d) {  // array_compar
 // being differentiated is the last one that feeds it): offer it to the sink.
 ArrayRef GraphAlgebra::try_gemm_sink(Id id, const ArrayRef& lhs, const ArrayRef& rhs, MatProp pl, MatProp pr) {
   if (!gemm_sink_ || id.arena != arena_id_ || id.index >= waiting_.size() || waiting_[id.index] != 1 || !is_variable(id)) return ArrayRef();
-  ArrayRef out = gemm_sink_(id, lhs, rhs, pl, pr);
+  // is any other large variable still waiting for contributions? if not, this product ends the sweep's heavy work
+  bool last = true;
+  for (size_t v = 1; v < waiting_.size() && last; v++)
+    if (v != id.index && waiting_[v] > 0 && !served_[v] && nodes_[v - 1].fwd_dims.elements() >= (1u << 20)) last = false;
+  ArrayRef out = gemm_sink_(id, lhs, rhs, pl, pr, last);
   if (out) served_[id.index] = 1;
   return out;
 }
