@@ -130,3 +130,17 @@ def test_product_never_touches_the_oracle():
     assert not bad, bad
     deps = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in deps
+
+
+def test_header_is_plain_c_and_the_c_demo_links():
+    """include/gadcu.h is usable from C (no C++-isms) and examples/c_abi_demo.c links against libgadcu.so."""
+    import shutil
+    import tempfile
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", os.path.join(root, "examples", "c_abi_demo.c"), "-I", os.path.join(root, "include"),
+                              "-L", os.path.dirname(_lib.LIB_PATH), "-lgadcu", "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH),
+                              "-o", os.path.join(tmp, "demo")], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
