@@ -246,3 +246,31 @@ def test_captured_step_replays_bit_identically(ctx):
     cap.launch()
     z1, gx1, gy1 = wl.c3_step(ctx, x, y)
     assert np.array_equal(gx.numpy(), gx1.numpy())
+
+
+def test_no_memory_growth_over_repeated_steps(ctx):
+    """The caching pool, the lane programs (one per tape epoch) and the split cache release what a step used:
+    after warm-up, 40 more mixed steps leave bytes-in-use and bytes-reserved unchanged."""
+    B, D = 512, 256
+    X, Ws, bs, T = _mlp_inputs(B, D)
+    dX, dT = ctx.array(X), ctx.array(T)
+    dW, db = [ctx.array(w) for w in Ws], [ctx.array(b) for b in bs]
+    n = 1 << 17
+    x, y = ctx.array(rand((n,), 3, -1, 1)), ctx.array(rand((n,), 4, 0.5, 2.0))
+    cols = [ctx.array(-1.2 + 2.4 * np.random.default_rng(i).random(4096)) for i in range(8)]
+
+    def one():
+        wl.mlp_step(ctx, dX, dW, db, dT)[0].item()
+        wl.c3_step(ctx, x, y)[0].item()
+        g, f, grads, store = wl.rosenbrock_batched_gradients(ctx, cols)
+        store.rerun(cols)
+
+    for _ in range(4):
+        one()
+    ctx.synchronize()
+    before = ctx.stats()
+    for _ in range(40):
+        one()
+    ctx.synchronize()
+    after = ctx.stats()
+    assert after["bytes_in_use"] == before["bytes_in_use"] and after["bytes_reserved"] == before["bytes_reserved"], (before, after)
