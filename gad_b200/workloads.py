@@ -93,9 +93,10 @@ def mlp_step(ctx: Context, X: CuArray, Ws: Sequence[CuArray], bs: Sequence[CuArr
     return lossd, gW, gb
 
 
-def mlp_hvp(ctx: Context, X: CuArray, Ws, bs, target: CuArray, vs: Sequence[CuArray]):
+def mlp_hvp(ctx: Context, X: CuArray, Ws, bs, target: CuArray, vs: Sequence[CuArray], comm: Optional[Comm] = None):
     """C5: Hessian-vector product of the MLP loss by reverse-over-reverse on GraphN:
-    g = grad L; s = sum_l dot(g_{W_l}, v_l); hv = grad s."""
+    g = grad L; s = sum_l dot(g_{W_l}, v_l); hv = grad s. The loss is a sum over batch rows, so with `comm` each rank
+    differentiates its rows twice and the products (and the loss) are summed over the ranks."""
     g = GraphN(ctx)
     loss, vW, vb = mlp_forward(g, X, Ws, bs, target)
     one = g.constant(ctx.scalar(1.0))
@@ -103,4 +104,7 @@ def mlp_hvp(ctx: Context, X: CuArray, Ws, bs, target: CuArray, vs: Sequence[CuAr
     terms = [g.dot(first.get(w.gid()), g.constant(v)) for w, v in zip(vW, vs)]
     s = g.add_all(terms)
     second = g.compute_gradients(s.gid(), one)
-    return [second.get(w.gid()).data() for w in vW], loss.data(), g.num_nodes()
+    hv, lossd = [second.get(w.gid()).data() for w in vW], loss.data()
+    if comm is not None and comm.nranks > 1:
+        comm.allreduce_sum(hv + [lossd])
+    return hv, lossd, g.num_nodes()
