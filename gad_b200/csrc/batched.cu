@@ -490,43 +490,63 @@ std::string gen_source(const SymProgram& P, const JitPlan& J, const std::unorder
     for (size_t k = 0; k < J.row.size(); k++) { in_slot[J.row[k].first] = J.row[k].second; tile_slot[J.row[k].first] = int(J.col.size() + k); }
     for (size_t k = 0; k < NO; k++) out_slot[J.outs[k]] = int(k);
     static const int min_blocks = [] { const char* e = getenv("GADCU_LANE_MINBLOCKS"); return e ? atoi(e) : 6; }();  // 6 x 128 threads: <= 80 registers, 24 warps per SM (measured best on C2)
+    // W lanes per thread: with two, every load / store is 128 bits wide (f64) and half as many threads carry the
+    // same bytes in flight
+    const int W = J.V;
+    const char* sfx[2] = {W == 1 ? "" : "_0", "_1"};
+    const char* comp[2] = {".x", ".y"};
+    o << "typedef " << (f32 ? "float2" : "double2") << " TV2;\n";
     o << "extern \"C\" __global__ void __launch_bounds__(" << J.block;
-    if (min_blocks > 0) o << ", " << min_blocks;
+    if (min_blocks > 0) o << ", " << (W == 1 ? min_blocks : std::max(1, min_blocks / 3));  // two lanes: 2 x 128 threads, ~200 registers, no spills
     o << ") lane_program(const P p) {\n";
     o << "  const u64 tid = (u64)blockIdx.x * " << J.block << "ull + threadIdx.x;\n  const u64 stride = (u64)gridDim.x * " << J.block << "ull;\n";
-    o << "  for (u64 i = tid; i < p.n; i += stride) {\n";
+    o << "  for (u64 i = tid; i < p.n / " << W << "; i += stride) {\n";
     for (int32_t r : J.sched) {
       const SymInstr& I = P.instrs[r];
       const bool cached = P.cache.count(r) != 0;
       if (cached || I.op == S_LOAD) {
-        o << "    const T " << reg_name(r) << " = __ldcs(p.in[" << in_slot.at(r) << "] + i);\n";
+        if (W == 1) {
+          o << "    const T " << reg_name(r) << " = __ldcs(p.in[" << in_slot.at(r) << "] + i);\n";
+        } else {
+          o << "    const TV2 v" << reg_name(r) << " = __ldcs(reinterpret_cast<const TV2*>(p.in[" << in_slot.at(r) << "]) + i);\n";
+          for (int l = 0; l < W; l++) o << "    const T " << reg_name(r) << sfx[l] << " = v" << reg_name(r) << comp[l] << ";\n";
+        }
       } else if (I.op == S_LOADU) {
-        o << "    const T " << reg_name(r) << " = p.in[" << in_slot.at(r) << "][0];\n";
+        for (int l = 0; l < W; l++) o << "    const T " << reg_name(r) << sfx[l] << " = p.in[" << in_slot.at(r) << "][0];\n";
       } else if (I.op == S_LOADCOL) {
         o << "    const T " << reg_name(r) << " = p.in[" << in_slot.at(r) << "][" << (J.idx32 ? "(unsigned)i / (unsigned)p.td[" : "i / p.td[") << tile_slot.at(r) << "]];\n";
       } else if (I.op == S_LOADROW) {
         o << "    const T " << reg_name(r) << " = p.in[" << in_slot.at(r) << "][" << (J.idx32 ? "(unsigned)i % (unsigned)p.td[" : "i % p.td[") << tile_slot.at(r) << "]];\n";
       } else {
         const char* e = op_expr(I.op);
-        std::string expr;
-        for (const char* c = e; *c; c++) {
-          if (*c == '%') {
-            c++;
-            switch (*c) {
-              case 'a': expr += reg_name(I.a); break;
-              case 'b': expr += reg_name(I.b); break;
-              case 'c': expr += reg_name(I.c); break;
-              case 'd': expr += reg_name(I.d); break;
-              case 'k': expr += "T(p.imm[" + std::to_string(imm_slot.at(r)) + "])"; break;
+        for (int l = 0; l < W; l++) {
+          std::string expr;
+          for (const char* c = e; *c; c++) {
+            if (*c == '%') {
+              c++;
+              switch (*c) {
+                case 'a': expr += reg_name(I.a) + sfx[l]; break;
+                case 'b': expr += reg_name(I.b) + sfx[l]; break;
+                case 'c': expr += reg_name(I.c) + sfx[l]; break;
+                case 'd': expr += reg_name(I.d) + sfx[l]; break;
+                case 'k': expr += "T(p.imm[" + std::to_string(imm_slot.at(r)) + "])"; break;
+              }
+            } else {
+              expr += *c;
             }
-          } else {
-            expr += *c;
           }
+          o << "    const T " << reg_name(r) << sfx[l] << " = " << expr << ";\n";
         }
-        o << "    const T " << reg_name(r) << " = " << expr << ";\n";
       }
       auto os = out_slot.find(r);
-      if (os != out_slot.end()) o << "    p.out[" << os->second << "][i] = " << reg_name(r) << ";\n";
+      if (os != out_slot.end()) {
+        if (W == 1) {
+          o << "    p.out[" << os->second << "][i] = " << reg_name(r) << ";\n";
+        } else {
+          o << "    { TV2 w; w.x = " << reg_name(r) << sfx[0] << "; w.y = " << reg_name(r) << sfx[1] << "; reinterpret_cast<TV2*>(p.out[" << os->second
+            << "])[i] = w; }\n";
+        }
+      }
     }
     o << "  }\n}\n";
     return o.str();
@@ -715,6 +735,8 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
     // greedy list scheduling for few live values: among the ready instructions take the one that ends the most
     // live ranges (net of the one it starts); prefer computing over loading, then tape order
     J.flat = true;
+    static const int lane_width = [] { const char* e = getenv("GADCU_LANE_WIDTH"); return e ? atoi(e) : 2; }();  // measured on C2: 0.249 ms with one lane per thread, 0.200 ms with two
+    if (lane_width == 2 && lanes % 2 == 0 && J.col.empty() && J.row.empty()) J.V = 2;
     std::vector<int32_t> nodes;  // needed registers, ascending
     for (int32_t r = 0; r < n; r++)
       if (needed[r]) nodes.push_back(r);
