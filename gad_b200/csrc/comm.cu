@@ -187,14 +187,15 @@ __global__ void dp_barrier_kernel(PeerFlags flags, int nranks, int rank, uint32_
 // column-major [M, N] gradient. 128-bit accesses; the peer stores travel over NVLink.
 struct PeerResults { float* p[8]; };
 __global__ void __launch_bounds__(256) dp_reduce_publish_kernel(const float4* __restrict__ staging, PeerResults results, uint32_t M,
-                                                                uint32_t num_mt, uint32_t tiles, uint32_t nranks, uint32_t rank) {
+                                                                uint32_t num_mt, uint32_t tiles, uint32_t nranks, uint32_t rank,
+                                                                uint32_t parts /* partial blocks per tile: nranks x k-splits */) {
   const uint32_t owned = tiles > rank ? (tiles - rank + nranks - 1) / nranks : 0;
   const uint64_t total = uint64_t(owned) * 16384u;  // float4s
   for (uint64_t i = uint64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += uint64_t(gridDim.x) * 256) {
     const uint32_t k = uint32_t(i >> 14), v = uint32_t(i & 16383u);
-    const float4* part = staging + (uint64_t(k) * nranks) * 16384u + v;
+    const float4* part = staging + (uint64_t(k) * parts) * 16384u + v;
     float4 acc = part[0];
-    for (uint32_t r = 1; r < nranks; r++) {
+    for (uint32_t r = 1; r < parts; r++) {
       const float4 x = part[uint64_t(r) * 16384u];
       acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
     }
@@ -380,7 +381,7 @@ ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, M
   if (!k::gemm_push_supported(g) || comm->no_peer_memory) return ArrayRef();
   const size_t bytes = size_t(g.M) * g.N * 4;
   try {
-    ensure_heap(comm, bytes);
+    ensure_heap(comm, 2 * bytes);  // (a k-split GEMM pushes two partial blocks per tile and rank)
   } catch (const GadError& e) {
     // no peer memory on this system (IPC disabled, no P2P): decline — the gradient then travels through the grouped
     // NCCL all-reduce at the end of the sweep like the small ones. Systemic, so every rank takes the same branch.
@@ -421,6 +422,7 @@ ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, M
     push.nranks = uint32_t(comm->nranks);
     push.rank = uint32_t(comm->rank);
     for (int r = 0; r < comm->nranks; r++) push.peer[r] = comm->heap.staging(r, slot);
+    push.splits = push_from_epilogue ? k::gemm_push_splits(ctx, gc) : 1;
     if (push_from_epilogue) gc.push = &push;
     mark(comm, "compute: gemm start", ctx->stream);
     k::launch_gemm(ctx, gc);  // compute stream; with the pushing epilogue the partial tiles land in their owners' staging buffers
@@ -450,7 +452,8 @@ ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, M
     if (owned > 0) {
       const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(owned) * 64, uint64_t(ctx->sm_count) * 4));
       dp_reduce_publish_kernel<<<grid, 256, 0, comm->stream>>>(reinterpret_cast<const float4*>(comm->heap.staging(comm->rank, slot)), res,
-                                                               uint32_t(g.M), num_mt, tiles, uint32_t(comm->nranks), uint32_t(comm->rank));
+                                                               uint32_t(g.M), num_mt, tiles, uint32_t(comm->nranks), uint32_t(comm->rank),
+                                                               uint32_t(comm->nranks) * push.splits);
       ctx->count_launch();
     }
     mark(comm, "comm: reduce+publish done", comm->stream);

@@ -347,14 +347,19 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
                : "memory");
 }
 
+// Tile order: bands of `band` tile-rows (or, with along_n, tile-columns) are walked one after the other; inside a band
+// the banded index runs fastest. The operand slices of the band stay in L2 while the other operand streams past once
+// per band, so the band goes along the dimension whose own operand is the SMALLER one to keep resident.
 struct TileSched {
-  uint32_t num_mt, num_nt, total, band_m;
+  uint32_t num_mt, num_nt, total, band, along_n;
   __device__ __forceinline__ void decode(uint32_t t, uint32_t& mt, uint32_t& nt) const {
-    const uint32_t band_size = band_m * num_nt;
-    const uint32_t band = t / band_size, r = t - band * band_size;
-    const uint32_t rows = min(band_m, num_mt - band * band_m);
-    nt = r / rows;
-    mt = band * band_m + (r - nt * rows);
+    const uint32_t banded = along_n ? num_nt : num_mt, other = along_n ? num_mt : num_nt;
+    const uint32_t band_size = band * other;
+    const uint32_t b = t / band_size, r = t - b * band_size;
+    const uint32_t rows = min(band, banded - b * band);
+    const uint32_t o = r / rows, i = b * band + (r - o * rows);
+    mt = along_n ? o : i;
+    nt = along_n ? i : o;
   }
 };
 
@@ -363,7 +368,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                         const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, float* __restrict__ C,
                         uint32_t M, uint32_t N, uint32_t K, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t accumulate,
-                        OperandLayout la, OperandLayout lb, uint32_t band_m, const GemmPush push) {
+                        OperandLayout la, OperandLayout lb, uint32_t band_m, uint32_t splits, const GemmPush push) {
   using cfg = Cfg2<BKT, S>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -379,8 +384,13 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const uint32_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const uint32_t num_kb = K / BKT;
-  TileSched sched{M / 256, N / 256, (M / 256) * (N / 256), band_m};
+  // A work unit is one output tile or, with splits == 2, one half of its k range (units 2t and 2t+1): when the tile
+  // count fills the last wave badly (256 tiles on 74 clusters: 3.46 waves cost 4), twice as many half-length units fill
+  // it well (6.92 cost 7). The two halves of a tile meet in C through red.add on a zeroed C (a + b in either order is
+  // the same float) or, in push mode, as two separate partial blocks that the owner adds in fixed order.
+  const uint32_t num_kb = K / BKT / splits;
+  TileSched sched{M / 256, N / 256, (M / 256) * (N / 256), band_m & 0xffffu, band_m >> 16};
+  const uint32_t total_units = sched.total * splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; s++) {
@@ -409,10 +419,11 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
     // ===== TMA producer: this CTA's halves of the A and B tiles =====
     if (lane == 0) {
       uint32_t it = 0;  // k-blocks issued so far (ring position)
-      for (uint32_t t = cluster_id; t < sched.total; t += num_clusters) {
+      for (uint32_t u = cluster_id; u < total_units; u += num_clusters) {
         uint32_t mt, nt;
-        sched.decode(t, mt, nt);
+        sched.decode(u / splits, mt, nt);
         const uint32_t m0 = mt * 256 + rank * 128, n0 = nt * 256 + rank * 128;
+        const uint32_t kb0 = (u % splits) * num_kb;
         for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
           const int s = it % S;
           const uint32_t phase = (it / S) & 1;
@@ -421,7 +432,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
           const uint32_t sa_h = stage, sa_l = stage + cfg::kTile, sb_h = stage + 2 * cfg::kTile, sb_l = stage + 3 * cfg::kTile;
           if (rank == 0) mbar_expect_tx(full_bar(s), 2 * cfg::kStageBytes);
           const uint32_t fb = mapa(full_bar(s), 0);
-          const int k0 = int(kb * BKT);
+          const int k0 = int((kb0 + kb) * BKT);
           if (a_mn_major) {
             tma2_load_3d(sa_h, &map_ah, fb, 0, k0, int(m0 / 32));
             tma2_load_3d(sa_l, &map_al, fb, 0, k0, int(m0 / 32));
@@ -445,7 +456,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
                              (uint32_t(256 >> 3) << 17) | (uint32_t(256 >> 4) << 24);
       uint32_t it = 0, ti = 0;
-      for (uint32_t t = cluster_id; t < sched.total; t += num_clusters, ti++) {
+      for (uint32_t u = cluster_id; u < total_units; u += num_clusters, ti++) {
         const uint32_t as = ti & 1, use = ti >> 1;
         mbar_wait(tmem_empty_bar(as), (use & 1) ^ 1);  // both epilogues have drained this accumulator
         tc_fence_after();
@@ -477,9 +488,10 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
     const int q = warp - 4;  // TMEM lane quarter this warp may read
     const uint32_t te = mapa(tmem_empty_bar(0), 0);
     uint32_t ti = 0;
-    for (uint32_t t = cluster_id; t < sched.total; t += num_clusters, ti++) {
+    for (uint32_t u = cluster_id; u < total_units; u += num_clusters, ti++) {
       uint32_t mt, nt;
-      sched.decode(t, mt, nt);
+      sched.decode(u / splits, mt, nt);
+      const uint32_t half = u % splits;
       const uint32_t as = ti & 1, use = ti >> 1;
       mbar_wait(tmem_full_bar(as), use & 1);
       tc_fence_after();
@@ -488,7 +500,8 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
         // fused reduce-scatter: this rank's partial tile goes to the staging buffer of the tile's owner, as a dense
         // 256 x 256 block (a warp store = 32 consecutive rows = 128 contiguous bytes over NVLink)
         const uint32_t tl = nt * sched.num_mt + mt;
-        float* dst = push.peer[tl % push.nranks] + (size_t(tl / push.nranks) * push.nranks + push.rank) * 65536u + rank * 128 + q * 32 + lane;
+        float* dst = push.peer[tl % push.nranks] + ((size_t(tl / push.nranks) * push.nranks + push.rank) * splits + half) * 65536u + rank * 128 +
+                     q * 32 + lane;
 #pragma unroll 1
         for (int c = 0; c < 256; c += 32) {
           uint32_t r[32];
@@ -506,11 +519,17 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
           tmem_ld32(taddr + uint32_t(c), r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            float* p = crow + size_t(c + j) * M;
-            float v = __uint_as_float(r[j]);
-            if (accumulate) v = *p + v;  // store.rs:52 `current + new`, fused into the epilogue
-            *p = v;
+          if (splits == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) atomicAdd(crow + size_t(c + j) * M, __uint_as_float(r[j]));  // (result unused: RED)
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              float* p = crow + size_t(c + j) * M;
+              float v = __uint_as_float(r[j]);
+              if (accumulate) v = *p + v;  // store.rs:52 `current + new`, fused into the epilogue
+              *p = v;
+            }
           }
         }
       }
@@ -628,6 +647,17 @@ bool gemm_tc_supported(const GemmArgs& g) {
 
 namespace {
 
+// split the k range in two when that fills the last wave markedly better (see the kernel)
+uint32_t choose_splits(gadcu_ctx* ctx, const GemmArgs& g, int bk) {
+  static const int split_mode = [] { const char* e = getenv("GADCU_GEMM_SPLITK"); return e ? atoi(e) : -1; }();  // -1 auto, 1 off, 2 force
+  const uint64_t tiles = (g.M / 256) * (g.N / 256), kb = g.K / uint64_t(bk);
+  if (g.accumulate || kb % 2 != 0 || kb / 2 < 8 || split_mode == 1) return 1;
+  if (split_mode == 2) return 2;
+  const uint64_t c = uint64_t(ctx->sm_count / 2);
+  auto wave_eff = [&](uint64_t units) { return double(units) / double((units + c - 1) / c * c); };
+  return wave_eff(2 * tiles) > wave_eff(tiles) + 0.05 ? 2 : 1;
+}
+
 template <int BKT, int S>
 void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float* al, const float* bh, const float* bl, bool a_mn,
                  bool b_mn) {
@@ -643,14 +673,26 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   // otherwise keep them out until the GEMM ends)
   static const uint64_t reserve = [] { const char* e = getenv("GADCU_DP_RESERVE_CLUSTERS"); return e ? uint64_t(atoi(e)) : uint64_t(0); }();
   const uint64_t usable = uint64_t(ctx->sm_count / 2) - (ctx->comm_inflight.load(std::memory_order_relaxed) ? reserve : 0);
-  const uint64_t clusters = std::min<uint64_t>(tiles, usable);
+  const uint64_t clusters = std::min<uint64_t>(tiles * 2, usable);  // (units = tiles or 2 x tiles; a cluster without a unit exits at once)
+  // band of tiles whose operand slices (hi + lo, 8 bytes per element) should fit in about half of L2 (126 MB), along
+  // the dimension with the smaller operand: that operand is then read from HBM once, the other once per band
+  static const uint32_t band_override = [] { const char* e = getenv("GADCU_GEMM_BAND"); return e ? uint32_t(atoi(e)) : 0u; }();
+  const uint64_t slice_bytes = 256ull * g.K * 8;  // one tile-row of A or tile-column of B
+  uint32_t band = uint32_t(std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(slice_bytes, 1)));
+  const uint32_t along_n = g.N < g.M ? 1u : 0u;   // fewer tile-columns than tile-rows: B is the smaller operand
+  band = std::min<uint32_t>(band, uint32_t((along_n ? g.N : g.M) / 256));
+  if (band_override) band = band_override & 0xffffu;
+  const uint32_t band_arg = band | ((band_override ? (band_override >> 16) : along_n) << 16);
+  uint32_t splits = choose_splits(ctx, g, BKT);
+  if (g.push) splits = g.push->splits;  // (the exchange laid its staging out for this)
+  if (splits == 2 && !g.push) GADCU_CUDA(cudaMemsetAsync(g.C, 0, size_t(g.M) * g.N * 4, ctx->stream));
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<BKT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BKT, S>::kSmem);
   });
   gemm_tf32x3_pair_kernel<BKT, S><<<unsigned(2 * clusters), kThreads2, Cfg2<BKT, S>::kSmem, ctx->stream>>>(
-      mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M), uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb, 8u,
-      g.push ? *g.push : GemmPush{});
+      mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M), uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb, band_arg,
+      splits, g.push ? *g.push : GemmPush{});
 }
 
 int pair_variant() {  // GADCU_GEMM_PAIR = off | 32x3 | 16x6 (default 32x3)
@@ -683,6 +725,8 @@ static const float* split_operand(gadcu_ctx* ctx, const float* x, uint64_t elems
   }
   return hi;
 }
+
+uint32_t gemm_push_splits(gadcu_ctx* ctx, const GemmArgs& g) { return choose_splits(ctx, g, pair_variant() == 1 ? 32 : 16); }
 
 bool gemm_push_supported(const GemmArgs& g) {
   return gemm_tc_supported(g) && pair_variant() != 0 && g.M % 256 == 0 && g.N % 256 == 0 && !g.accumulate;

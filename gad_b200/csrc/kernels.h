@@ -77,6 +77,7 @@ void launch_random(gadcu_ctx* ctx, gadcu_dtype dt, void* out, uint64_t n, uint64
 struct GemmPush {
   float* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // staging base of every rank
   uint32_t nranks = 0, rank = 0;
+  uint32_t splits = 1;  // partial blocks per (tile, rank): 2 when the GEMM splits its k range (gemm_push_splits)
 };
 
 // C[M,N] (+)= op(A) * op(B), column-major; batch over `batch` matrices with element strides (0 = broadcast).
@@ -97,6 +98,7 @@ struct GemmArgs {
 void launch_gemm(gadcu_ctx* ctx, const GemmArgs& g);
 bool gemm_tc_supported(const GemmArgs& g);  // tcgen05 3xTF32 path applies
 bool gemm_push_supported(const GemmArgs& g);  // ... and its CTA-pair kernel, which can push tiles to peers
+uint32_t gemm_push_splits(gadcu_ctx* ctx, const GemmArgs& g);  // 1 or 2: how the pair kernel would split k for this shape
 
 }  // namespace k
 }  // namespace gadcu
