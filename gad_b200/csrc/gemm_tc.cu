@@ -384,7 +384,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const uint32_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  // A work unit is one output tile or, with splits == 2, one half of its k range (units 2t and 2t+1): when the tile
+  // A work unit is one output tile or, with splits == 2, one half of its k range (units t and total + t): when the tile
   // count fills the last wave badly (256 tiles on 74 clusters: 3.46 waves cost 4), twice as many half-length units fill
   // it well (6.92 cost 7). The two halves of a tile meet in C through red.add on a zeroed C (a + b in either order is
   // the same float) or, in push mode, as two separate partial blocks that the owner adds in fixed order.
@@ -421,9 +421,9 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
       uint32_t it = 0;  // k-blocks issued so far (ring position)
       for (uint32_t u = cluster_id; u < total_units; u += num_clusters) {
         uint32_t mt, nt;
-        sched.decode(u / splits, mt, nt);
+        sched.decode(u % sched.total, mt, nt);  // all first halves, then all second halves: a wave's operand slices are half as long
         const uint32_t m0 = mt * 256 + rank * 128, n0 = nt * 256 + rank * 128;
-        const uint32_t kb0 = (u % splits) * num_kb;
+        const uint32_t kb0 = (u / sched.total) * num_kb;
         for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
           const int s = it % S;
           const uint32_t phase = (it / S) & 1;
@@ -490,8 +490,8 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
     uint32_t ti = 0;
     for (uint32_t u = cluster_id; u < total_units; u += num_clusters, ti++) {
       uint32_t mt, nt;
-      sched.decode(u / splits, mt, nt);
-      const uint32_t half = u % splits;
+      sched.decode(u % sched.total, mt, nt);
+      const uint32_t half = u / sched.total;
       const uint32_t as = ti & 1, use = ti >> 1;
       mbar_wait(tmem_full_bar(as), use & 1);
       tc_fence_after();
@@ -677,7 +677,7 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   // band of tiles whose operand slices (hi + lo, 8 bytes per element) should fit in about half of L2 (126 MB), along
   // the dimension with the smaller operand: that operand is then read from HBM once, the other once per band
   static const uint32_t band_override = [] { const char* e = getenv("GADCU_GEMM_BAND"); return e ? uint32_t(atoi(e)) : 0u; }();
-  const uint64_t slice_bytes = 256ull * g.K * 8;  // one tile-row of A or tile-column of B
+  const uint64_t slice_bytes = 256ull * (g.K / choose_splits(ctx, g, BKT)) * 8;  // one tile-row of A or tile-column of B (of one k half)
   uint32_t band = uint32_t(std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(slice_bytes, 1)));
   const uint32_t along_n = g.N < g.M ? 1u : 0u;   // fewer tile-columns than tile-rows: B is the smaller operand
   band = std::min<uint32_t>(band, uint32_t((along_n ? g.N : g.M) / 256));
