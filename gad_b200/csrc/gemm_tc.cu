@@ -311,17 +311,21 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+// L2 eviction policies (the encodings createpolicy.fractional.L2::evict_{first,last} produces for fraction 1.0): the
+// operand whose slices a band of tiles keeps re-reading stays, the one that streams past once per band goes first.
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull, kEvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
-__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
           dst),
-      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t smem_slot, uint32_t ncols) {
@@ -389,7 +393,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
   // it well (6.92 cost 7). The two halves of a tile meet in C through red.add on a zeroed C (a + b in either order is
   // the same float) or, in push mode, as two separate partial blocks that the owner adds in fixed order.
   const uint32_t num_kb = K / BKT / splits;
-  TileSched sched{M / 256, N / 256, (M / 256) * (N / 256), band_m & 0xffffu, band_m >> 16};
+  TileSched sched{M / 256, N / 256, (M / 256) * (N / 256), band_m & 0xffffu, (band_m >> 16) & 1u};
   const uint32_t total_units = sched.total * splits;
 
   if (threadIdx.x == 0) {
@@ -419,6 +423,13 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
     // ===== TMA producer: this CTA's halves of the A and B tiles =====
     if (lane == 0) {
       uint32_t it = 0;  // k-blocks issued so far (ring position)
+      // bands along N keep B's slices hot and stream A past them; bands along M the other way round
+      // (measured: evict_first on the streaming operand more than doubles the DRAM reads — the tiles of a wave share
+      // its slices through L2 — so the streaming side keeps the normal policy; hints 0 = none, 1 = resident evict_last)
+      const uint32_t hints = band_m >> 17;
+      constexpr uint64_t kNormal = 0x1000000000000000ull;
+      const uint64_t pol_a = hints == 0 ? kNormal : (sched.along_n ? (hints == 2 ? kEvictFirst : kNormal) : kEvictLast);
+      const uint64_t pol_b = hints == 0 ? kNormal : (sched.along_n ? kEvictLast : (hints == 2 ? kEvictFirst : kNormal));
       for (uint32_t u = cluster_id; u < total_units; u += num_clusters) {
         uint32_t mt, nt;
         sched.decode(u % sched.total, mt, nt);  // all first halves, then all second halves: a wave's operand slices are half as long
@@ -434,18 +445,18 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
           const uint32_t fb = mapa(full_bar(s), 0);
           const int k0 = int((kb0 + kb) * BKT);
           if (a_mn_major) {
-            tma2_load_3d(sa_h, &map_ah, fb, 0, k0, int(m0 / 32));
-            tma2_load_3d(sa_l, &map_al, fb, 0, k0, int(m0 / 32));
+            tma2_load_3d(sa_h, &map_ah, fb, 0, k0, int(m0 / 32), pol_a);
+            tma2_load_3d(sa_l, &map_al, fb, 0, k0, int(m0 / 32), pol_a);
           } else {
-            tma2_load_2d(sa_h, &map_ah, fb, k0, int(m0));
-            tma2_load_2d(sa_l, &map_al, fb, k0, int(m0));
+            tma2_load_2d(sa_h, &map_ah, fb, k0, int(m0), pol_a);
+            tma2_load_2d(sa_l, &map_al, fb, k0, int(m0), pol_a);
           }
           if (b_mn_major) {
-            tma2_load_3d(sb_h, &map_bh, fb, 0, k0, int(n0 / 32));
-            tma2_load_3d(sb_l, &map_bl, fb, 0, k0, int(n0 / 32));
+            tma2_load_3d(sb_h, &map_bh, fb, 0, k0, int(n0 / 32), pol_b);
+            tma2_load_3d(sb_l, &map_bl, fb, 0, k0, int(n0 / 32), pol_b);
           } else {
-            tma2_load_2d(sb_h, &map_bh, fb, k0, int(n0));
-            tma2_load_2d(sb_l, &map_bl, fb, k0, int(n0));
+            tma2_load_2d(sb_h, &map_bh, fb, k0, int(n0), pol_b);
+            tma2_load_2d(sb_l, &map_bl, fb, k0, int(n0), pol_b);
           }
         }
       }
@@ -682,7 +693,8 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   const uint32_t along_n = g.N < g.M ? 1u : 0u;   // fewer tile-columns than tile-rows: B is the smaller operand
   band = std::min<uint32_t>(band, uint32_t((along_n ? g.N : g.M) / 256));
   if (band_override) band = band_override & 0xffffu;
-  const uint32_t band_arg = band | ((band_override ? (band_override >> 16) : along_n) << 16);
+  static const uint32_t l2_hints = [] { const char* e = getenv("GADCU_GEMM_L2_HINTS"); return e ? uint32_t(atoi(e)) & 3u : 0u; }();
+  const uint32_t band_arg = band | (((band_override ? (band_override >> 16) : along_n) & 1u) << 16) | (l2_hints << 17);
   uint32_t splits = choose_splits(ctx, g, BKT);
   if (g.push) splits = g.push->splits;  // (the exchange laid its staging out for this)
   if (splits == 2 && !g.push) GADCU_CUDA(cudaMemsetAsync(g.C, 0, size_t(g.M) * g.N * 4, ctx->stream));
