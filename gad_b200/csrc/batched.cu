@@ -257,6 +257,11 @@ void launch_interpreter(gadcu_ctx* ctx, int slots, const DevInstr* prog, int n, 
 }
 
 // ---- compile (DCE + liveness slot assignment) and run -------------------------------------------
+// Kernel parameters may be up to 32 764 bytes on sm_70+ (CUDA 12.1+); one pointer per input / output column, one
+// double per constant. Requests with more outputs than fit are computed in several kernels.
+constexpr size_t kMaxParamBytes = 32000;
+constexpr size_t kMaxOutputsPerKernel = 1024;
+
 bool use_jit() {
   static const bool interp = [] {
     const char* e = getenv("GADCU_LANES");
@@ -277,7 +282,12 @@ std::vector<ArrayRef> SymProgram::run(const std::vector<int32_t>& outs) {
   if (todo.empty()) return result;
   std::sort(todo.begin(), todo.end());
   todo.erase(std::unique(todo.begin(), todo.end()), todo.end());
-  std::vector<ArrayRef> cols = (array_mode || use_jit()) ? run_jit(todo) : run_interpreter(todo);
+  std::vector<ArrayRef> cols;
+  for (size_t first = 0; first < todo.size(); first += kMaxOutputsPerKernel) {
+    const std::vector<int32_t> part(todo.begin() + first, todo.begin() + std::min(todo.size(), first + kMaxOutputsPerKernel));
+    std::vector<ArrayRef> c = (array_mode || use_jit()) ? run_jit(part) : run_interpreter(part);
+    cols.insert(cols.end(), c.begin(), c.end());
+  }
   for (size_t j = 0; j < todo.size(); j++) cache[todo[j]] = cols[j];
   for (size_t i = 0; i < outs.size(); i++)
     if (!result[i]) result[i] = cache[outs[i]];
@@ -885,7 +895,7 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
     }
     kernel = jit::compile(key, src, "lane_program");
   }
-  if (reusable && J.imms.size() * 8 + (J.in_ptrs.size() + J.outs.size() + J.tile_d0.size() + 1) * 8 <= 4000) {
+  if (reusable && J.imms.size() * 8 + (J.in_ptrs.size() + J.outs.size() + J.tile_d0.size() + 1) * 8 <= kMaxParamBytes) {
     Compiled c;
     c.kernel = kernel;
     c.in_inputs = J.in_inputs;
@@ -907,7 +917,7 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   params[NI + NO] = lanes;
   for (size_t i = 0; i < J.tile_d0.size(); i++) params[NI + NO + 1 + i] = J.tile_d0[i];
   for (size_t i = 0; i < J.imms.size(); i++) std::memcpy(&params[NI + NO + 1 + NT + i], &J.imms[i], 8);
-  if (params.size() * 8 > 4000) fail(GADCU_ERR_UNSUPPORTED, "lane program has too many inputs / outputs / constants for one kernel");
+  if (params.size() * 8 > kMaxParamBytes) fail(GADCU_ERR_UNSUPPORTED, "lane program has too many inputs / outputs / constants for one kernel");
   const uint64_t per_block = uint64_t(J.block) * uint64_t(J.V) * uint64_t(J.U);
   uint64_t grid = (lanes + per_block - 1) / per_block;
   const uint64_t cap = uint64_t(ctx->sm_count) * (J.block == 256 ? 8 : 16);

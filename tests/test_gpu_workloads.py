@@ -56,6 +56,16 @@ def test_batched_rerun_at_new_points_equals_a_fresh_tape(ctx, oracle):
         store.rerun([ctx.array(x1[0])])
 
 
+def test_wide_batched_tape_beyond_4k_of_kernel_parameters(ctx, oracle):
+    """Rosenbrock-320: 320 input and 320 output columns (5 KB of pointers) + 640 constants in one lane program."""
+    n, lanes = 320, 64
+    x = -1.2 + 2.4 * np.random.default_rng(11).random((n, lanes))
+    g, f, grads, store = wl.rosenbrock_batched_gradients(ctx, [ctx.array(x[i]) for i in range(n)])
+    got = np.stack([to_np(c)[:, 0, 0, 0] for c in grads])
+    _, ograd, _ = oracle.rosenbrock_batch(x, nthreads=4)
+    assert np.array_equal(got, ograd)
+
+
 def test_batched_tape_golden_point_and_f32(ctx):
     cols = [ctx.array(np.array([-1.2, 1.0])), ctx.array(np.array([1.0, 1.0]))]
     g, f, grads, _ = wl.rosenbrock_batched_gradients(ctx, cols)
