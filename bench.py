@@ -154,7 +154,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = host_cores()
-    rows = 128
+    rows = 512  # ~4 s per step on 16 cores
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_mlp_steps_per_s(rows, threads)
     vals, times = [], []
@@ -341,7 +341,7 @@ def run_ours(args):
             line["secondary"] = {"error": repr(e)}
         try:
             threads = host_cores()
-            rows_s = 128
+            rows_s = 1024  # ~10 s of CPU work on 16 cores: one eighth of the batch at full width, all L layers
             v, t = cpu_mlp_steps_per_s(rows_s, threads)
             line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "seconds": t,
                                     "sample": f"{rows_s} of {B_TOTAL} batch rows at full width D={D}, L={L}; scaled by {B_TOTAL // rows_s}x"}
