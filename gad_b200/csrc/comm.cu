@@ -422,7 +422,9 @@ ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, M
     push.nranks = uint32_t(comm->nranks);
     push.rank = uint32_t(comm->rank);
     for (int r = 0; r < comm->nranks; r++) push.peer[r] = comm->heap.staging(r, slot);
-    push.splits = push_from_epilogue ? k::gemm_push_splits(ctx, gc) : 1;
+    // a k-split GEMM pushes two partial blocks per tile: a gain up to 4 ranks (4 GPUs: 342 -> 350 steps/s), but at 8 the
+    // pushes are what the NVLink-bound exchange waits for (517 -> 480), so there the GEMM keeps whole tiles
+    push.splits = push_from_epilogue && comm->nranks <= 4 ? k::gemm_push_splits(ctx, gc) : 1;
     if (push_from_epilogue) gc.push = &push;
     mark(comm, "compute: gemm start", ctx->stream);
     k::launch_gemm(ctx, gc);  // compute stream; with the pushing epilogue the partial tiles land in their owners' staging buffers
