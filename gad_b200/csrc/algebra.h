@@ -15,8 +15,15 @@ namespace gadcu {
 
 const std::string& last_error();
 
+// Every entry point of the C ABI runs under one process-wide recursive lock: handles may be shared between host
+// threads (gad's types are Send + Sync, and evaluate_gradients(&self) may be called from several threads on one tape,
+// lib.rs:69-72), and a context issues all its work on one stream with shared scratch buffers, so calls are serialised
+// rather than made lock-free. Recursive because a user-defined VJP (gadcu_make_node) calls back into the API.
+std::recursive_mutex& api_mutex();
+
 template <class F>
 gadcu_status guard(F f) {
+  std::lock_guard<std::recursive_mutex> api_lock(api_mutex());
   try {
     f();
     return GADCU_OK;

@@ -644,9 +644,15 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
   heap.push(gid);
   Id guard = gid.next_id();
   // final-gradient hook: how many nodes still have to run before a variable's gradient is complete
-  std::vector<uint32_t>& waiting = waiting_;  // by node index; only variables are counted
-  waiting.clear();
-  served_.clear();
+  // (member state is touched only by hooked — data-parallel — sweeps; plain evaluate_gradients(&self) stays re-entrant
+  // from several threads, graph.rs:263-274)
+  const bool hooked = bool(final_hook_) && ga.is_eval();
+  std::vector<uint32_t> unhooked;
+  std::vector<uint32_t>& waiting = hooked ? waiting_ : unhooked;  // by node index; only variables are counted
+  if (hooked) {
+    waiting.clear();
+    served_.clear();
+  }
   auto distinct_variable_inputs = [&](const Node& nd, std::vector<uint32_t>& out) {
     out.clear();
     for (auto& in : nd.inputs) {
@@ -657,7 +663,7 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
     }
   };
   std::vector<uint32_t> scratch;
-  if (final_hook_ && ga.is_eval()) {
+  if (hooked) {
     waiting.assign(nodes_.size() + 1, 0);
     for (auto& nd : nodes_) {
       if (!nd.has_update) continue;
@@ -667,7 +673,7 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
   }
   std::vector<char> fired(waiting.size(), 0), was_variable(waiting.size(), 0);  // (a consuming sweep resets the nodes it passes)
   for (size_t i = 1; i < was_variable.size(); i++) was_variable[i] = nodes_[i - 1].op == Op::VARIABLE && !nodes_[i - 1].has_update;
-  served_.assign(waiting.size(), 0);
+  if (hooked) served_.assign(waiting.size(), 0);
   while (!heap.empty()) {
     Id id = heap.top();
     heap.pop();
@@ -714,7 +720,7 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
       if (vid.arena == arena_id_ && vid.index < fired.size() && was_variable[vid.index] && !fired[vid.index] && !served_[vid.index] && kv.second.data)
         final_hook_(vid, kv.second.data);
     }
-  waiting_.clear();
+  if (hooked) waiting_.clear();
   return store;
 }
 

@@ -57,6 +57,11 @@ void Pool::put(void* p, size_t bytes) {
   in_use -= bytes;
 }
 
+std::recursive_mutex& api_mutex() {
+  static std::recursive_mutex m;
+  return m;
+}
+
 void Buffer::release() {
   if (refs.fetch_sub(1, std::memory_order_acq_rel) == 1) {
     if (split) split->release();

@@ -284,3 +284,32 @@ def test_no_memory_growth_over_repeated_steps(ctx):
     ctx.synchronize()
     after = ctx.stats()
     assert after["bytes_in_use"] == before["bytes_in_use"] and after["bytes_reserved"] == before["bytes_reserved"], (before, after)
+
+
+def test_one_tape_swept_from_several_threads(ctx):
+    """gad's graphs are Send + Sync and evaluate_gradients(&self) does not modify the tape (lib.rs:69-72,
+    graph.rs:263-274): four host threads sweep the same tape with different seeds at the same time."""
+    import threading
+    n = 100_003
+    x, y = rand((n,), 3, -1, 1), rand((n,), 4, 0.5, 2.0)
+    g = gb.Graph1(ctx)
+    vx, vy, z = wl.c3_forward(g, ctx.array(x), ctx.array(y))
+    want = g.evaluate_gradients(z.gid(), 1.0).get(vx.gid()).numpy()
+    results, errors = {}, []
+
+    def work(k):
+        try:
+            for _ in range(5):
+                s = g.evaluate_gradients(z.gid(), float(2 ** k))
+                results[k] = s.get(vx.gid()).numpy()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(4):
+        assert np.array_equal(results[k], want * np.float32(2 ** k))
