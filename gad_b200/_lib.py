@@ -71,6 +71,7 @@ SIGNATURES = {
     "gadcu_comm_allreduce_sum_async": (C.c_int, [P, PP, C.c_size_t]),
     "gadcu_comm_join": (C.c_int, [P]),
     "gadcu_evaluate_gradients_dp": (C.c_int, [P, C.c_uint32, C.c_uint32, P, C.c_int, P, PP]),
+    "gadcu_evaluate_gradients_dp_with": (C.c_int, [P, C.c_uint32, C.c_uint32, P, C.c_int, P, PP, C.c_size_t, PP]),
     "gadcu_batched_rerun": (C.c_int, [P, PP, C.c_size_t, PP]),
     "gadcu_array_upload": (C.c_int, [P, P, P]),
     "gadcu_array_upload_async": (C.c_int, [P, P]),

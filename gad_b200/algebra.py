@@ -625,13 +625,17 @@ class Graph1(_DeviceAlgebra):
         _check(self.lib.gadcu_evaluate_gradients(self.handle, gid.arena, gid.index, seed.handle, 0, C.byref(h)))
         return Store(self.ctx, h, values=False)
 
-    def evaluate_gradients_once(self, gid: GradientId, gradient, comm: Optional["Comm"] = None) -> Store:  # graph.rs:279-290
+    def evaluate_gradients_once(self, gid: GradientId, gradient, comm: Optional["Comm"] = None,
+                                also_reduce: Sequence[CuArray] = ()) -> Store:  # graph.rs:279-290
         """With `comm`: the sweep of one batch shard — every variable's gradient is summed over the ranks as soon as
-        the sweep has completed it (gadcu_evaluate_gradients_dp), overlapping the rest of the sweep."""
+        the sweep has completed it (gadcu_evaluate_gradients_dp), overlapping the rest of the sweep; `also_reduce`
+        (the step's loss) rides in the same small exchange as the bias gradients."""
         h = C.c_void_p()
         seed = self._seed(gradient)
         if comm is not None and comm.nranks > 1:
-            _check(self.lib.gadcu_evaluate_gradients_dp(self.handle, gid.arena, gid.index, seed.handle, 1, comm.handle, C.byref(h)))
+            also = (C.c_void_p * max(1, len(also_reduce)))(*[a.handle for a in also_reduce])
+            _check(self.lib.gadcu_evaluate_gradients_dp_with(self.handle, gid.arena, gid.index, seed.handle, 1, comm.handle, also,
+                                                             len(also_reduce), C.byref(h)))
         else:
             _check(self.lib.gadcu_evaluate_gradients(self.handle, gid.arena, gid.index, seed.handle, 1, C.byref(h)))
         return Store(self.ctx, h, values=False)

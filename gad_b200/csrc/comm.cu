@@ -523,6 +523,10 @@ gadcu_status gadcu_comm_join(gadcu_comm* comm) {
 // are still being differentiated — and the compute stream waits for all of them before the call returns.
 gadcu_status gadcu_evaluate_gradients_dp(gadcu_algebra* g, uint32_t arena, uint32_t index, gadcu_array* seed, int once, gadcu_comm* comm,
                                          gadcu_store** out) {
+  return gadcu_evaluate_gradients_dp_with(g, arena, index, seed, once, comm, nullptr, 0, out);
+}
+gadcu_status gadcu_evaluate_gradients_dp_with(gadcu_algebra* g, uint32_t arena, uint32_t index, gadcu_array* seed, int once, gadcu_comm* comm,
+                                              gadcu_array* const* also, size_t n_also, gadcu_store** out) {
   return guard([&] {
     if (index == 0) fail(GADCU_ERR_MISSING_ID, "Trying to obtain `id` of a constant value.");
     auto* graph = dynamic_cast<GraphAlgebra*>(g);
@@ -547,6 +551,7 @@ gadcu_status gadcu_evaluate_gradients_dp(gadcu_algebra* g, uint32_t arena, uint3
       graph->set_final_hook(nullptr);
       graph->set_gemm_sink(nullptr);
       if (!dp) return;
+      for (size_t i = 0; i < n_also; i++) comm->deferred.emplace_back(also[i], true);
       if (!comm->deferred.empty()) {
         std::vector<gadcu_array*> raw;
         for (auto& a : comm->deferred) raw.push_back(a.get());

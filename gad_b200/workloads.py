@@ -85,11 +85,11 @@ def mlp_step(ctx: Context, X: CuArray, Ws: Sequence[CuArray], bs: Sequence[CuArr
     loss, vW, vb = mlp_forward(g, X, Ws, bs, target)
     lossd = loss.data()
     dp = comm is not None and comm.nranks > 1
-    store = g.evaluate_gradients_once(loss.gid(), 1.0, comm if overlap else None)
+    store = g.evaluate_gradients_once(loss.gid(), 1.0, comm if overlap else None, [lossd] if dp and overlap else ())
     gW = [store.get(v.gid()) for v in vW]
     gb = [store.get(v.gid()) for v in vb]
-    if dp:
-        comm.allreduce_sum([lossd] if overlap else gW + gb + [lossd])
+    if dp and not overlap:
+        comm.allreduce_sum(gW + gb + [lossd])
     return lossd, gW, gb
 
 

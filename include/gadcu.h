@@ -272,6 +272,9 @@ GADCU_API gadcu_status gadcu_comm_join(gadcu_comm* comm);
  * comm == NULL or a 1-rank communicator: identical to gadcu_evaluate_gradients. */
 GADCU_API gadcu_status gadcu_evaluate_gradients_dp(gadcu_algebra* g, uint32_t arena, uint32_t index, gadcu_array* seed, int once,
                                                    gadcu_comm* comm, gadcu_store** out);
+/* Same, and `also` (e.g. the loss of the step) is summed over the ranks in the same small exchange as the bias gradients. */
+GADCU_API gadcu_status gadcu_evaluate_gradients_dp_with(gadcu_algebra* g, uint32_t arena, uint32_t index, gadcu_array* seed, int once,
+                                                        gadcu_comm* comm, gadcu_array* const* also, size_t n_also, gadcu_store** out);
 GADCU_API gadcu_status gadcu_comm_destroy(gadcu_comm* comm);
 
 #ifdef __cplusplus
