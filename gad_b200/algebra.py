@@ -258,6 +258,8 @@ class CuArray:
         return CuArray(self.ctx, h)
 
     def upload(self, pinned: np.ndarray, stream: int = 0) -> None:
+        """Overwrite the device buffer with `pinned`'s bytes as they lie: the host data must already be in the device
+        layout (column-major, i.e. `np.asfortranarray(x).ravel(order="K")` or `x.reshape(-1, order="F")`)."""
         _check(self.ctx.lib.gadcu_array_upload(self.handle, pinned.ctypes.data_as(C.c_void_p), C.c_void_p(stream or None)))
 
     def upload_async(self, pinned: np.ndarray) -> None:

@@ -313,3 +313,30 @@ def test_one_tape_swept_from_several_threads(ctx):
     assert not errors, errors
     for k in range(4):
         assert np.array_equal(results[k], want * np.float32(2 ** k))
+
+
+def test_captured_mlp_step_replays_bit_identically(ctx):
+    """A whole C4 step — tcgen05 GEMMs (TMA maps, split kernels, split-K memsets), compiled elementwise regions,
+    reductions — captured into one CUDA graph and replayed: same loss and gradients as the eager step, and the
+    replay follows new contents of the input buffers."""
+    B, D = 512, 256
+    X, Ws, bs, T = _mlp_inputs(B, D)
+    dX, dT = ctx.array(X), ctx.array(T)
+    dW, db = [ctx.array(w) for w in Ws], [ctx.array(b) for b in bs]
+    eager = wl.mlp_step(ctx, dX, dW, db, dT)
+    want_loss, want_W = eager[0].item(), [g.numpy() for g in eager[1]]
+    with gb.Capture(ctx) as cap:
+        out = wl.mlp_step(ctx, dX, dW, db, dT)
+    for _ in range(2):
+        cap.launch()
+    ctx.synchronize()
+    assert out[0].item() == want_loss
+    for a, b in zip(out[1], want_W):
+        assert np.array_equal(a.numpy(), b)
+    X2 = _mlp_inputs(B, D, seed=17)[0]
+    dX.upload(np.ascontiguousarray(X2.reshape(-1, order="F")))   # upload takes the device (column-major) layout
+    ctx.synchronize()
+    cap.launch()
+    fresh = wl.mlp_step(ctx, ctx.array(X2), dW, db, dT)
+    assert out[0].item() == fresh[0].item()
+    assert np.array_equal(out[1][2].numpy(), fresh[1][2].numpy())
