@@ -112,6 +112,7 @@ struct gadcu_ctx {
   void* pinned_scratch = nullptr;  // 4 KiB pinned staging for scalar reads
   void* dev_scratch = nullptr;     // reduction partials
   size_t dev_scratch_bytes = 0;
+  uint32_t* gemm_flags = nullptr;  // stream-K hand-over flags (gemm_tc.cu): 8 per split tile, zero between launches
   std::mutex mu;
   // optional per-category kernel timing with CUDA events on `stream` (bench.py's roofline figures)
   bool profiling = false;

@@ -367,12 +367,72 @@ struct TileSched {
   }
 };
 
+// What a cluster works on. First the data-parallel units u = c, c+G, ... (one output tile each or, with splits == 2,
+// one k half of a tile: tile = u % total, half = u / total). Then the ragged last wave of `rem` < G tiles, stream-K
+// fashion but k-ALIGNED: cluster c < rem takes k-blocks [0, KB - r) of tile c (all of them sweep k in lockstep, as in
+// a full wave, so the operand slices they share are fetched from HBM once), and the G - rem clusters that would have
+// idled take the tails [KB - r, KB) of those tiles, `ceil(rem / (G - rem))` each (a window of k small enough to stay in
+// L2). r is chosen so both kinds finish together: 64 tiles on 74 clusters cost 0.875 of a tile time instead of 1,
+// 256 tiles 3.5 instead of 4. (Cutting the tiles' k-blocks into contiguous equal ranges, the textbook stream-K,
+// measured SLOWER than idling: clusters at different k offsets share nothing in L2 and the GEMM went DRAM-bound.)
+struct Work {
+  uint32_t tile, half, kb0, kb1, part;  // k-blocks [kb0, kb1) of `tile`; part: 0 whole unit, 1 tail (stores first), 2 head (adds)
+};
+struct StreamK {
+  uint32_t rem, tail_kb;
+  uint32_t* flags;  // 8 per tile of the last wave (one per epilogue warp of the pair), all zero between launches
+  unsigned long long* trace;  // debugging (GADCU_SK_TRACE): per cluster and work item, 4 timestamps of epilogue warp 0
+};
+struct WorkIter {
+  uint32_t u, dp_units, stride, total, unit_kb;
+  uint32_t next_tile, end_tile, tile_step, kb0, kb1, part;
+  __device__ __forceinline__ WorkIter(uint32_t cluster, uint32_t clusters, uint32_t total_tiles, uint32_t splits, uint32_t kb_per_tile,
+                                      const StreamK& sk)
+      : u(cluster), dp_units((total_tiles - sk.rem) * splits), stride(clusters), total(total_tiles - sk.rem),
+        unit_kb(kb_per_tile / splits), end_tile(total_tiles) {
+    if (sk.rem == 0) {
+      next_tile = end_tile;
+    } else if (cluster < sk.rem) {
+      next_tile = total + cluster, tile_step = total_tiles;  // (one item)
+      kb0 = 0, kb1 = kb_per_tile - sk.tail_kb, part = 2;
+    } else {
+      next_tile = total + (cluster - sk.rem), tile_step = clusters - sk.rem;
+      kb0 = kb_per_tile - sk.tail_kb, kb1 = kb_per_tile, part = 1;
+    }
+  }
+  __device__ __forceinline__ bool next(Work& w) {
+    if (u < dp_units) {
+      const uint32_t half = u / total;
+      w = Work{u - half * total, half, half * unit_kb, (half + 1) * unit_kb, 0u};
+      u += stride;
+      return true;
+    }
+    if (next_tile >= end_tile) return false;
+    w = Work{next_tile, 0u, kb0, kb1, part};
+    next_tile += tile_step;
+    return true;
+  }
+};
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int BKT, int S>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                         const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, float* __restrict__ C,
                         uint32_t M, uint32_t N, uint32_t K, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t accumulate,
-                        OperandLayout la, OperandLayout lb, uint32_t band_m, uint32_t splits, const GemmPush push) {
+                        OperandLayout la, OperandLayout lb, uint32_t band_m, uint32_t splits, const StreamK sk, const GemmPush push) {
   using cfg = Cfg2<BKT, S>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -392,9 +452,9 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
   // count fills the last wave badly (256 tiles on 74 clusters: 3.46 waves cost 4), twice as many half-length units fill
   // it well (6.92 cost 7). The two halves of a tile meet in C through red.add on a zeroed C (a + b in either order is
   // the same float) or, in push mode, as two separate partial blocks that the owner adds in fixed order.
-  const uint32_t num_kb = K / BKT / splits;
+  // (splits == 2 is used by the tile-pushing mode, and without it only when stream-K is switched off)
+  const uint32_t num_kb = K / BKT;
   TileSched sched{M / 256, N / 256, (M / 256) * (N / 256), band_m & 0xffffu, (band_m >> 16) & 1u};
-  const uint32_t total_units = sched.total * splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; s++) {
@@ -430,12 +490,13 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
       constexpr uint64_t kNormal = 0x1000000000000000ull;
       const uint64_t pol_a = hints == 0 ? kNormal : (sched.along_n ? (hints == 2 ? kEvictFirst : kNormal) : kEvictLast);
       const uint64_t pol_b = hints == 0 ? kNormal : (sched.along_n ? kEvictLast : (hints == 2 ? kEvictFirst : kNormal));
-      for (uint32_t u = cluster_id; u < total_units; u += num_clusters) {
+      WorkIter work(cluster_id, num_clusters, sched.total, splits, num_kb, sk);
+      Work w;
+      while (work.next(w)) {
         uint32_t mt, nt;
-        sched.decode(u % sched.total, mt, nt);  // all first halves, then all second halves: a wave's operand slices are half as long
+        sched.decode(w.tile, mt, nt);  // (all first halves, then all second halves: a wave's operand slices are half as long)
         const uint32_t m0 = mt * 256 + rank * 128, n0 = nt * 256 + rank * 128;
-        const uint32_t kb0 = (u / sched.total) * num_kb;
-        for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
+        for (uint32_t kb = w.kb0; kb < w.kb1; kb++, it++) {
           const int s = it % S;
           const uint32_t phase = (it / S) & 1;
           mbar_wait(empty_bar(s), phase ^ 1);
@@ -443,7 +504,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
           const uint32_t sa_h = stage, sa_l = stage + cfg::kTile, sb_h = stage + 2 * cfg::kTile, sb_l = stage + 3 * cfg::kTile;
           if (rank == 0) mbar_expect_tx(full_bar(s), 2 * cfg::kStageBytes);
           const uint32_t fb = mapa(full_bar(s), 0);
-          const int k0 = int((kb0 + kb) * BKT);
+          const int k0 = int(kb * BKT);
           if (a_mn_major) {
             tma2_load_3d(sa_h, &map_ah, fb, 0, k0, int(m0 / 32), pol_a);
             tma2_load_3d(sa_l, &map_al, fb, 0, k0, int(m0 / 32), pol_a);
@@ -467,12 +528,14 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
                              (uint32_t(256 >> 3) << 17) | (uint32_t(256 >> 4) << 24);
       uint32_t it = 0, ti = 0;
-      for (uint32_t u = cluster_id; u < total_units; u += num_clusters, ti++) {
+      WorkIter work(cluster_id, num_clusters, sched.total, splits, num_kb, sk);
+      Work w;
+      for (; work.next(w); ti++) {
         const uint32_t as = ti & 1, use = ti >> 1;
         mbar_wait(tmem_empty_bar(as), (use & 1) ^ 1);  // both epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * kAccCols;
-        for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
+        for (uint32_t kb = w.kb0; kb < w.kb1; kb++, it++) {
           const int s = it % S;
           const uint32_t phase = (it / S) & 1;
           mbar_wait(full_bar(s), phase);
@@ -485,7 +548,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
             const uint64_t dal = make_smem_desc(sa_l + k * la.kstep, la.lbo, la.sbo, la.layout);
             const uint64_t dbh = make_smem_desc(sb_h + k * lb.kstep, lb.lbo, lb.sbo, lb.layout);
             const uint64_t dbl = make_smem_desc(sb_l + k * lb.kstep, lb.lbo, lb.sbo, lb.layout);
-            umma2_tf32(tmem_d, dal, dbh, idesc, (kb | uint32_t(k)) != 0);  // small terms first
+            umma2_tf32(tmem_d, dal, dbh, idesc, ((kb - w.kb0) | uint32_t(k)) != 0);  // small terms first
             umma2_tf32(tmem_d, dah, dbl, idesc, 1);
             umma2_tf32(tmem_d, dah, dbh, idesc, 1);
           }
@@ -499,13 +562,19 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
     const int q = warp - 4;  // TMEM lane quarter this warp may read
     const uint32_t te = mapa(tmem_empty_bar(0), 0);
     uint32_t ti = 0;
-    for (uint32_t u = cluster_id; u < total_units; u += num_clusters, ti++) {
+    WorkIter work(cluster_id, num_clusters, sched.total, splits, num_kb, sk);
+    Work w;
+    for (; work.next(w); ti++) {
       uint32_t mt, nt;
-      sched.decode(u % sched.total, mt, nt);
-      const uint32_t half = u / sched.total;
+      sched.decode(w.tile, mt, nt);
+      const uint32_t half = w.half;
       const uint32_t as = ti & 1, use = ti >> 1;
+      const bool tracing = sk.trace && rank == 0 && q == 0 && lane == 0 && ti < 16;
+      unsigned long long* tr = sk.trace + (size_t(cluster_id) * 16 + ti) * 4;
+      if (tracing) tr[0] = global_timer_ns();
       mbar_wait(tmem_full_bar(as), use & 1);
       tc_fence_after();
+      if (tracing) tr[1] = global_timer_ns();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * kAccCols;
       if (push.nranks) {
         // fused reduce-scatter: this rank's partial tile goes to the staging buffer of the tile's owner, as a dense
@@ -521,6 +590,44 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
 #pragma unroll
           for (int j = 0; j < 32; j++) dst[size_t(c + j) * 256] = __uint_as_float(r[j]);
         }
+      } else if (w.part) {
+        // one of the two parts of a last-wave tile: the tail stores (C + acc with `accumulate`) and raises the flag of
+        // ITS 32 rows; the head waits for it and stores C + acc. Two terms, so the sum does not depend on who was first;
+        // the tail of a tile is among the first things its cluster does, so the wait is short and cannot form a cycle.
+        const bool head = w.part == 2;
+        uint32_t* flag = sk.flags + ((w.tile - (sched.total - sk.rem)) * 8 + rank * 4 + q);
+        if (head) {
+          if (lane == 0) {
+            const uint64_t t0 = global_timer_ns();
+            while (ld_acquire_gpu(flag) != 1u)
+              if (global_timer_ns() - t0 > 4000000000ull) __trap();  // a lost partner must not hang the GPU
+          }
+          __syncwarp();
+        }
+        if (tracing) tr[2] = global_timer_ns();
+        const uint32_t row = mt * 256 + rank * 128 + q * 32 + lane;
+        float* crow = C + row + size_t(nt) * 256 * M;
+        const bool add = head || accumulate;
+#pragma unroll 1
+        for (int c = 0; c < 256; c += 32) {
+          uint32_t r[32];
+          float cur[32];
+          if (add) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) cur[j] = __ldcg(crow + size_t(c + j) * M);  // (all 32 in flight; L2, not a stale L1 line)
+          }
+          tmem_ld32(taddr + uint32_t(c), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) crow[size_t(c + j) * M] = add ? cur[j] + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+        }
+        if (!head) {
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) st_release_gpu(flag, 1u);
+        } else if (lane == 0) {
+          *flag = 0;  // ready for the next launch
+        }
       } else {
         const uint32_t row = mt * 256 + rank * 128 + q * 32 + lane;
         float* crow = C + row + size_t(nt) * 256 * M;
@@ -529,24 +636,25 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
           uint32_t r[32];
           tmem_ld32(taddr + uint32_t(c), r);
           tmem_ld_wait();
-#pragma unroll
           if (splits == 2) {
 #pragma unroll
             for (int j = 0; j < 32; j++) atomicAdd(crow + size_t(c + j) * M, __uint_as_float(r[j]));  // (result unused: RED)
+          } else if (accumulate) {  // store.rs:52 `current + new`, fused into the epilogue
+            float cur[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) cur[j] = crow[size_t(c + j) * M];
+#pragma unroll
+            for (int j = 0; j < 32; j++) crow[size_t(c + j) * M] = cur[j] + __uint_as_float(r[j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              float* p = crow + size_t(c + j) * M;
-              float v = __uint_as_float(r[j]);
-              if (accumulate) v = *p + v;  // store.rs:52 `current + new`, fused into the epilogue
-              *p = v;
-            }
+            for (int j = 0; j < 32; j++) crow[size_t(c + j) * M] = __uint_as_float(r[j]);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(te + 8u * as);
+      if (tracing) tr[3] = global_timer_ns();
     }
   }
   tc_fence_before();
@@ -684,19 +792,37 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   // otherwise keep them out until the GEMM ends)
   static const uint64_t reserve = [] { const char* e = getenv("GADCU_DP_RESERVE_CLUSTERS"); return e ? uint64_t(atoi(e)) : uint64_t(0); }();
   const uint64_t usable = uint64_t(ctx->sm_count / 2) - (ctx->comm_inflight.load(std::memory_order_relaxed) ? reserve : 0);
-  const uint64_t clusters = std::min<uint64_t>(tiles * 2, usable);  // (units = tiles or 2 x tiles; a cluster without a unit exits at once)
+  // the ragged last wave is shared out stream-K fashion (see WorkIter; GADCU_GEMM_STREAMK=0 for the older split-in-two)
+  static const bool streamk_on = [] { const char* e = getenv("GADCU_GEMM_STREAMK"); return !e || atoi(e) != 0; }();
+  static const uint64_t min_tail = [] { const char* e = getenv("GADCU_GEMM_SK_MIN_TAIL"); return e ? uint64_t(atoi(e)) : uint64_t(8); }();
+  const bool streamk = streamk_on && !g.push && ctx->gemm_flags != nullptr;
+  const uint64_t kb_per_tile = g.K / BKT;
+  const uint64_t clusters = std::min<uint64_t>(tiles * 2, usable);  // (a cluster without work exits at once)
+  StreamK sk{0u, 0u, ctx->gemm_flags, nullptr};
+  if (streamk && tiles % clusters != 0) {
+    const uint64_t rem = tiles % clusters, helpers = clusters - rem, per_helper = (rem + helpers - 1) / helpers;
+    const uint64_t tail = kb_per_tile / (per_helper + 1);  // head (KB - tail) = per_helper tails
+    if (tail >= min_tail) sk.rem = uint32_t(rem), sk.tail_kb = uint32_t(tail);  // (shorter tails: the epilogues would dominate)
+  }
+  static const int trace_at = [] { const char* e = getenv("GADCU_SK_TRACE"); return e ? atoi(e) : 0; }();  // trace the n-th launch
+  static int trace_count = 0;
+  const bool trace_on = trace_at && ++trace_count == trace_at;
+  if (trace_on) {
+    GADCU_CUDA(cudaMallocManaged(&sk.trace, 74 * 16 * 4 * 8));
+    memset(sk.trace, 0, 74 * 16 * 4 * 8);
+  }
   // band of tiles whose operand slices (hi + lo, 8 bytes per element) should fit in about half of L2 (126 MB), along
   // the dimension with the smaller operand: that operand is then read from HBM once, the other once per band
   static const uint32_t band_override = [] { const char* e = getenv("GADCU_GEMM_BAND"); return e ? uint32_t(atoi(e)) : 0u; }();
-  const uint64_t slice_bytes = 256ull * (g.K / choose_splits(ctx, g, BKT)) * 8;  // one tile-row of A or tile-column of B (of one k half)
+  uint32_t splits = streamk ? 1u : choose_splits(ctx, g, BKT);
+  if (g.push) splits = g.push->splits;  // (the exchange laid its staging out for this)
+  const uint64_t slice_bytes = 256ull * (g.K / splits) * 8;  // one tile-row of A or tile-column of B (of one k half)
   uint32_t band = uint32_t(std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(slice_bytes, 1)));
   const uint32_t along_n = g.N < g.M ? 1u : 0u;   // fewer tile-columns than tile-rows: B is the smaller operand
   band = std::min<uint32_t>(band, uint32_t((along_n ? g.N : g.M) / 256));
   if (band_override) band = band_override & 0xffffu;
   static const uint32_t l2_hints = [] { const char* e = getenv("GADCU_GEMM_L2_HINTS"); return e ? uint32_t(atoi(e)) & 3u : 0u; }();
   const uint32_t band_arg = band | (((band_override ? (band_override >> 16) : along_n) & 1u) << 16) | (l2_hints << 17);
-  uint32_t splits = choose_splits(ctx, g, BKT);
-  if (g.push) splits = g.push->splits;  // (the exchange laid its staging out for this)
   if (splits == 2 && !g.push) GADCU_CUDA(cudaMemsetAsync(g.C, 0, size_t(g.M) * g.N * 4, ctx->stream));
   static std::once_flag once;
   std::call_once(once, [] {
@@ -704,7 +830,23 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   });
   gemm_tf32x3_pair_kernel<BKT, S><<<unsigned(2 * clusters), kThreads2, Cfg2<BKT, S>::kSmem, ctx->stream>>>(
       mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M), uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb, band_arg,
-      splits, g.push ? *g.push : GemmPush{});
+      splits, sk, g.push ? *g.push : GemmPush{});
+  if (trace_on) {
+    cudaStreamSynchronize(ctx->stream);
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < 74 * 16 * 4; i++) if (sk.trace[i] && sk.trace[i] < t0) t0 = sk.trace[i];
+    fprintf(stderr, "sk trace M=%llu N=%llu K=%llu clusters=%llu rem=%u tail_kb=%u\n", (unsigned long long)g.M, (unsigned long long)g.N,
+            (unsigned long long)g.K, (unsigned long long)clusters, sk.rem, sk.tail_kb);
+    for (int c = 0; c < 74; c++) {
+      fprintf(stderr, " c%02d:", c);
+      for (int w = 0; w < 16 && sk.trace[(c * 16 + w) * 4]; w++) {
+        unsigned long long* t = sk.trace + (c * 16 + w) * 4;
+        fprintf(stderr, " [%.1f full %.1f waited %.1f done %.1f]", (t[0] - t0) / 1e3, (t[1] - t0) / 1e3, t[2] ? (t[2] - t0) / 1e3 : 0.0, (t[3] - t0) / 1e3);
+      }
+      fprintf(stderr, "\n");
+    }
+    cudaFree(sk.trace);
+  }
 }
 
 int pair_variant() {  // GADCU_GEMM_PAIR = off | 32x3 | 16x6 (default 32x3)

@@ -148,6 +148,8 @@ gadcu_status gadcu_ctx_create(int device, gadcu_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->pool = std::make_shared<Pool>();
     GADCU_CUDA(cudaMallocHost(&ctx->pinned_scratch, 4096));
+    GADCU_CUDA(cudaMalloc(&ctx->gemm_flags, 4096));  // (fewer split tiles than SM pairs: 8 x 74 words)
+    GADCU_CUDA(cudaMemset(ctx->gemm_flags, 0, 4096));
     *out = ctx;
   });
 }
@@ -160,6 +162,7 @@ gadcu_status gadcu_ctx_destroy(gadcu_ctx* ctx) {
     cudaStreamSynchronize(ctx->side_stream);
     if (ctx->pinned_scratch) cudaFreeHost(ctx->pinned_scratch);
     if (ctx->dev_scratch) cudaFree(ctx->dev_scratch);
+    if (ctx->gemm_flags) cudaFree(ctx->gemm_flags);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->side_stream);
     delete ctx;
