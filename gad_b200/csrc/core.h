@@ -157,7 +157,7 @@ struct Buffer {
   // and reused by the other GEMMs of the same tape (every GEMM operand of the MLP step is read twice:
   // forward and one backward product). Valid for one tape epoch and until the buffer is written in place.
   Buffer* split = nullptr;
-  uint64_t split_epoch = 0, split_elems = 0;
+  uint64_t split_epoch = 0, split_elems = 0, split_rows = 0;
   void mutated();  // call after every in-place write: drops the cached split
   void retain() { refs.fetch_add(1, std::memory_order_relaxed); }
   void release();

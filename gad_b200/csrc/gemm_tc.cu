@@ -453,8 +453,11 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
   // it well (6.92 cost 7). The two halves of a tile meet in C through red.add on a zeroed C (a + b in either order is
   // the same float) or, in push mode, as two separate partial blocks that the owner adds in fixed order.
   // (splits == 2 is used by the tile-pushing mode, and without it only when stream-K is switched off)
-  const uint32_t num_kb = K / BKT;
-  TileSched sched{M / 256, N / 256, (M / 256) * (N / 256), band_m & 0xffffu, (band_m >> 16) & 1u};
+  // M, N, K need not be multiples of the tile: the tensor maps carry the true extents (TMA fills what lies outside with
+  // zeros, which add nothing to the product) and the epilogue stores only rows < M and columns < N.
+  const uint32_t num_kb = (K + BKT - 1) / BKT;
+  const uint32_t num_mt = (M + 255) / 256, num_nt = (N + 255) / 256;
+  TileSched sched{num_mt, num_nt, num_mt * num_nt, band_m & 0xffffu, (band_m >> 16) & 1u};
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; s++) {
@@ -590,10 +593,12 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
 #pragma unroll
           for (int j = 0; j < 32; j++) dst[size_t(c + j) * 256] = __uint_as_float(r[j]);
         }
-      } else if (w.part) {
-        // one of the two parts of a last-wave tile: the tail stores (C + acc with `accumulate`) and raises the flag of
-        // ITS 32 rows; the head waits for it and stores C + acc. Two terms, so the sum does not depend on who was first;
-        // the tail of a tile is among the first things its cluster does, so the wait is short and cannot form a cycle.
+      } else {
+        // How this unit's accumulator meets C: stored, added to what is there (`accumulate`: store.rs:52 `current + new`
+        // fused into the epilogue; or the second part of a last-wave tile), or red.add (split-in-two on a zeroed C).
+        // The two parts of a last-wave tile: the tail stores and raises the flag of ITS 32 rows; the head waits for it
+        // and stores C + acc. Two terms, so the sum does not depend on who came first; the tail of a tile is among the
+        // first things its cluster does, so the wait is short and cannot form a cycle.
         const bool head = w.part == 2;
         uint32_t* flag = sk.flags + ((w.tile - (sched.total - sk.rem)) * 8 + rank * 4 + q);
         if (head) {
@@ -606,49 +611,40 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
         }
         if (tracing) tr[2] = global_timer_ns();
         const uint32_t row = mt * 256 + rank * 128 + q * 32 + lane;
+        const bool row_ok = row < M;
+        const uint32_t ncols = min(256u, N - nt * 256);
         float* crow = C + row + size_t(nt) * 256 * M;
-        const bool add = head || accumulate;
+        const bool add = head || accumulate, red = splits == 2;
 #pragma unroll 1
-        for (int c = 0; c < 256; c += 32) {
+        for (uint32_t c = 0; c < ncols; c += 32) {
           uint32_t r[32];
           float cur[32];
-          if (add) {
+          const uint32_t nj = ncols - c;  // (columns left: all 32 of the chunk unless this is N's ragged edge)
+          if (add && row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) cur[j] = __ldcg(crow + size_t(c + j) * M);  // (all 32 in flight; L2, not a stale L1 line)
+            for (int j = 0; j < 32; j++)
+              if (uint32_t(j) < nj) cur[j] = __ldcg(crow + size_t(c + j) * M);  // (all in flight at once; L2, never a stale L1 line)
           }
-          tmem_ld32(taddr + uint32_t(c), r);
+          tmem_ld32(taddr + c, r);
           tmem_ld_wait();
+          if (row_ok) {
+            if (red) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) crow[size_t(c + j) * M] = add ? cur[j] + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+              for (int j = 0; j < 32; j++)
+                if (uint32_t(j) < nj) atomicAdd(crow + size_t(c + j) * M, __uint_as_float(r[j]));  // (result unused: RED)
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (uint32_t(j) < nj) crow[size_t(c + j) * M] = add ? cur[j] + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+            }
+          }
         }
-        if (!head) {
+        if (w.part == 1) {
           __threadfence();
           __syncwarp();
           if (lane == 0) st_release_gpu(flag, 1u);
-        } else if (lane == 0) {
+        } else if (head && lane == 0) {
           *flag = 0;  // ready for the next launch
-        }
-      } else {
-        const uint32_t row = mt * 256 + rank * 128 + q * 32 + lane;
-        float* crow = C + row + size_t(nt) * 256 * M;
-#pragma unroll 1
-        for (int c = 0; c < 256; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + uint32_t(c), r);
-          tmem_ld_wait();
-          if (splits == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) atomicAdd(crow + size_t(c + j) * M, __uint_as_float(r[j]));  // (result unused: RED)
-          } else if (accumulate) {  // store.rs:52 `current + new`, fused into the epilogue
-            float cur[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) cur[j] = crow[size_t(c + j) * M];
-#pragma unroll
-            for (int j = 0; j < 32; j++) crow[size_t(c + j) * M] = cur[j] + __uint_as_float(r[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j++) crow[size_t(c + j) * M] = __uint_as_float(r[j]);
-          }
         }
       }
       tc_fence_before();
@@ -682,6 +678,23 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restric
 #undef GADCU_SPLIT
     hi[i] = h;
     lo[i] = l;
+  }
+}
+
+// the same for a column-major [R, C] operand whose rows do not make whole 128-byte lines (or whose base is not 16-byte
+// aligned): the copies get a leading dimension of Rp = R rounded up to 32, the padding zero, so TMA can address them
+__global__ void __launch_bounds__(256) split_tf32_pad_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                                                             uint64_t R, uint64_t Rp, uint64_t n_out) {
+  const uint64_t stride = uint64_t(gridDim.x) * 256;
+  for (uint64_t i = uint64_t(blockIdx.x) * 256 + threadIdx.x; i < n_out; i += stride) {
+    const uint64_t c = i / Rp, r = i - c * Rp;
+    const float v = r < R ? __ldcs(x + c * R + r) : 0.0f;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+    const float h = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v - h));
+    hi[i] = h;
+    lo[i] = __uint_as_float(t);
   }
 }
 
@@ -732,14 +745,29 @@ CUtensorMap make_map(const float* base, bool mn_major, uint64_t mn, uint64_t kdi
   return map;
 }
 
-void split(gadcu_ctx* ctx, const float* x, float* hi, float* lo, uint64_t n) {
-  const uint64_t nvec = n / 4;
-  uint64_t blocks = (nvec + 255) / 256;
+void split(gadcu_ctx* ctx, const float* x, float* hi, float* lo, uint64_t R, uint64_t C, uint64_t Rp) {
   const uint64_t cap = uint64_t(ctx->sm_count) * 8;
-  if (blocks > cap) blocks = cap;
-  split_tf32_kernel<<<unsigned(blocks), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi),
-                                                              reinterpret_cast<float4*>(lo), nvec);
+  if (R == Rp && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const uint64_t nvec = R * C / 4;
+    const uint64_t blocks = std::min((nvec + 255) / 256, cap);
+    split_tf32_kernel<<<unsigned(blocks), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi),
+                                                                reinterpret_cast<float4*>(lo), nvec);
+  } else {
+    const uint64_t n_out = Rp * C;
+    const uint64_t blocks = std::min((n_out + 255) / 256, cap * 2);
+    split_tf32_pad_kernel<<<unsigned(blocks), 256, 0, ctx->stream>>>(x, hi, lo, R, Rp, n_out);
+  }
   ctx->count_launch();
+}
+
+int pair_variant() {  // GADCU_GEMM_PAIR = off | 32x3 | 16x6 (default 32x3)
+  static int v = [] {
+    const char* e = getenv("GADCU_GEMM_PAIR");
+    if (!e) return 1;
+    const std::string s(e);
+    return s == "off" ? 0 : s == "16x6" ? 2 : s == "16x4" ? 3 : 1;
+  }();
+  return v;
 }
 
 int tc_mode() {  // GADCU_GEMM=simt disables the tensor-core path (A/B testing)
@@ -754,14 +782,15 @@ int tc_mode() {  // GADCU_GEMM=simt disables the tensor-core path (A/B testing)
 
 bool gemm_tc_supported(const GemmArgs& g) {
   if (!tc_mode()) return false;
-  if (g.dt != GADCU_F32 || g.batch != 1) return false;
-  if (g.M % 128 || g.N % 128 || g.K % BK || g.K == 0) return false;
-  // the stored matrices must tile exactly (whole-matrix operands, 16-byte aligned rows)
+  if (g.dt != GADCU_F32 || g.batch != 1 || g.K == 0) return false;
+  // the stored matrices must be whole (leading dimension = rows)
   const uint64_t a_rows = g.ta ? g.K : g.M, b_rows = g.tb ? g.N : g.K;
   if (g.lda != a_rows || g.ldb != b_rows) return false;
-  if ((reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.B) | reinterpret_cast<uintptr_t>(g.C)) & 15) return false;
   if (g.M >= (1ull << 31) || g.N >= (1ull << 31) || g.K >= (1ull << 31)) return false;
-  return true;
+  if (g.M % 128 == 0 && g.N % 128 == 0 && g.K % BK == 0) return true;
+  // ragged shapes go through the pair kernel (edge tiles zero-filled by TMA, predicated stores) when the product is big
+  // enough for 256 x 256 tiles to pay; small or skinny ones stay on the CUDA-core kernel
+  return pair_variant() != 0 && g.M >= 64 && g.N >= 64 && g.K >= 32 && g.M * g.N * g.K >= (1ull << 24);
 }
 
 namespace {
@@ -770,6 +799,7 @@ namespace {
 uint32_t choose_splits(gadcu_ctx* ctx, const GemmArgs& g, int bk) {
   static const int split_mode = [] { const char* e = getenv("GADCU_GEMM_SPLITK"); return e ? atoi(e) : -1; }();  // -1 auto, 1 off, 2 force
   const uint64_t tiles = (g.M / 256) * (g.N / 256), kb = g.K / uint64_t(bk);
+  if (g.M % 256 || g.N % 256 || g.K % uint64_t(bk)) return 1;
   if (g.accumulate || kb % 2 != 0 || kb / 2 < 8 || split_mode == 1) return 1;
   if (split_mode == 2) return 2;
   const uint64_t c = uint64_t(ctx->sm_count / 2);
@@ -779,15 +809,17 @@ uint32_t choose_splits(gadcu_ctx* ctx, const GemmArgs& g, int bk) {
 
 template <int BKT, int S>
 void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float* al, const float* bh, const float* bl, bool a_mn,
-                 bool b_mn) {
+                 bool b_mn, uint64_t lda, uint64_t ldb /* leading dimensions of the split copies (multiples of 32) */) {
   // K-major tiles have rows of BKT*4 bytes: 128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B (8-row groups either way)
   const OperandLayout k_layout = BKT == 32 ? OperandLayout{16u, 1024u, UMMA_K * 4u, 2u} : OperandLayout{16u, 512u, UMMA_K * 4u, 4u};
   const CUtensorMapSwizzle k_swz = BKT == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const OperandLayout mn_layout{BKT * 128u, 512u, 1024u, 1u};
   const OperandLayout la = a_mn ? mn_layout : k_layout, lb = b_mn ? mn_layout : k_layout;
-  CUtensorMap mah = make_map(ah, a_mn, g.M, g.K, g.lda, 128, BKT, k_swz), mal = make_map(al, a_mn, g.M, g.K, g.lda, 128, BKT, k_swz);
-  CUtensorMap mbh = make_map(bh, b_mn, g.N, g.K, g.ldb, 128, BKT, k_swz), mbl = make_map(bl, b_mn, g.N, g.K, g.ldb, 128, BKT, k_swz);
-  const uint64_t tiles = (g.M / 256) * (g.N / 256);
+  // extents as stored: the contiguous dimension is the padded one (zeros), the strided one is exact (TMA zero-fills past it)
+  const uint64_t a_mn_ext = a_mn ? lda : g.M, a_k_ext = a_mn ? g.K : lda, b_mn_ext = b_mn ? ldb : g.N, b_k_ext = b_mn ? g.K : ldb;
+  CUtensorMap mah = make_map(ah, a_mn, a_mn_ext, a_k_ext, lda, 128, BKT, k_swz), mal = make_map(al, a_mn, a_mn_ext, a_k_ext, lda, 128, BKT, k_swz);
+  CUtensorMap mbh = make_map(bh, b_mn, b_mn_ext, b_k_ext, ldb, 128, BKT, k_swz), mbl = make_map(bl, b_mn, b_mn_ext, b_k_ext, ldb, 128, BKT, k_swz);
+  const uint64_t tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256);
   // while an overlapped all-reduce is in flight a few SM pairs are left to its CTAs (a persistent CTA per SM would
   // otherwise keep them out until the GEMM ends)
   static const uint64_t reserve = [] { const char* e = getenv("GADCU_DP_RESERVE_CLUSTERS"); return e ? uint64_t(atoi(e)) : uint64_t(0); }();
@@ -796,7 +828,7 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   static const bool streamk_on = [] { const char* e = getenv("GADCU_GEMM_STREAMK"); return !e || atoi(e) != 0; }();
   static const uint64_t min_tail = [] { const char* e = getenv("GADCU_GEMM_SK_MIN_TAIL"); return e ? uint64_t(atoi(e)) : uint64_t(8); }();
   const bool streamk = streamk_on && !g.push && ctx->gemm_flags != nullptr;
-  const uint64_t kb_per_tile = g.K / BKT;
+  const uint64_t kb_per_tile = (g.K + BKT - 1) / BKT;
   const uint64_t clusters = std::min<uint64_t>(tiles * 2, usable);  // (a cluster without work exits at once)
   StreamK sk{0u, 0u, ctx->gemm_flags, nullptr};
   if (streamk && tiles % clusters != 0) {
@@ -819,7 +851,7 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   const uint64_t slice_bytes = 256ull * (g.K / splits) * 8;  // one tile-row of A or tile-column of B (of one k half)
   uint32_t band = uint32_t(std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(slice_bytes, 1)));
   const uint32_t along_n = g.N < g.M ? 1u : 0u;   // fewer tile-columns than tile-rows: B is the smaller operand
-  band = std::min<uint32_t>(band, uint32_t((along_n ? g.N : g.M) / 256));
+  band = std::min<uint32_t>(band, uint32_t(((along_n ? g.N : g.M) + 255) / 256));
   if (band_override) band = band_override & 0xffffu;
   static const uint32_t l2_hints = [] { const char* e = getenv("GADCU_GEMM_L2_HINTS"); return e ? uint32_t(atoi(e)) & 3u : 0u; }();
   const uint32_t band_arg = band | (((band_override ? (band_override >> 16) : along_n) & 1u) << 16) | (l2_hints << 17);
@@ -849,33 +881,27 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   }
 }
 
-int pair_variant() {  // GADCU_GEMM_PAIR = off | 32x3 | 16x6 (default 32x3)
-  static int v = [] {
-    const char* e = getenv("GADCU_GEMM_PAIR");
-    if (!e) return 1;
-    const std::string s(e);
-    return s == "off" ? 0 : s == "16x6" ? 2 : s == "16x4" ? 3 : 1;
-  }();
-  return v;
-}
-
 }  // namespace
 
-// [hi | lo] of one operand: from the owning buffer's cache when it has a current one, else a fresh split that
-// is left on the buffer for the other GEMMs of this tape. `keep` holds the split alive until the launch is issued.
-static const float* split_operand(gadcu_ctx* ctx, const float* x, uint64_t elems, Buffer* owner, ArrayRef& keep) {
+// [hi | lo] of one operand (stored column-major [R, C]): from the owning buffer's cache when it has a current one, else
+// a fresh split that is left on the buffer for the other GEMMs of this tape. The copies have leading dimension
+// `ld` = R rounded up to 32 (see split_tf32_pad_kernel). `keep` holds the split alive until the launch is issued.
+static const float* split_operand(gadcu_ctx* ctx, const float* x, uint64_t R, uint64_t C, Buffer* owner, ArrayRef& keep, uint64_t& ld) {
+  ld = (R + 31) / 32 * 32;
+  const uint64_t elems = ld * C;
   const uint64_t epoch = ctx->epoch.load(std::memory_order_relaxed);
-  if (owner && owner->split && owner->split_epoch == epoch && owner->split_elems == elems)
+  if (owner && owner->split && owner->split_epoch == epoch && owner->split_elems == elems && owner->split_rows == R)
     return static_cast<const float*>(owner->split->ptr);
   keep = new_array(ctx, GADCU_F32, Dim4(2 * elems));
   float* hi = static_cast<float*>(keep->ptr());
-  split(ctx, x, hi, hi + elems, elems);
+  split(ctx, x, hi, hi + elems, R, C, ld);
   if (owner && !ctx->capturing) {
     owner->mutated();
     owner->split = keep->buf.get();
     owner->split->retain();
     owner->split_epoch = epoch;
     owner->split_elems = elems;
+    owner->split_rows = R;
   }
   return hi;
 }
@@ -887,19 +913,20 @@ bool gemm_push_supported(const GemmArgs& g) {
 }
 
 void launch_gemm_tc(gadcu_ctx* ctx, const GemmArgs& g) {
-  const uint64_t a_elems = g.M * g.K, b_elems = g.K * g.N;
-  ArrayRef keep_a, keep_b;
-  const float* ah = split_operand(ctx, static_cast<const float*>(g.A), a_elems, g.a_buf, keep_a);
-  const float* bh = split_operand(ctx, static_cast<const float*>(g.B), b_elems, g.b_buf, keep_b);
-  const float *al = ah + a_elems, *bl = bh + b_elems;
-
   const bool a_mn = !g.ta;  // stored [M,K] col-major: M contiguous
   const bool b_mn = g.tb;   // stored [N,K] col-major: N contiguous
-  if (pair_variant() && g.M % 256 == 0 && g.N % 256 == 0) {
+  ArrayRef keep_a, keep_b;
+  uint64_t lda = 0, ldb = 0;
+  const float* ah = split_operand(ctx, static_cast<const float*>(g.A), a_mn ? g.M : g.K, a_mn ? g.K : g.M, g.a_buf, keep_a, lda);
+  const float* bh = split_operand(ctx, static_cast<const float*>(g.B), b_mn ? g.N : g.K, b_mn ? g.K : g.N, g.b_buf, keep_b, ldb);
+  const float *al = ah + lda * (a_mn ? g.K : g.M), *bl = bh + ldb * (b_mn ? g.K : g.N);
+
+  const bool ragged = g.M % 128 != 0 || g.N % 128 != 0 || g.K % BK != 0;
+  if (pair_variant() && (ragged || (g.M % 256 == 0 && g.N % 256 == 0))) {
     switch (pair_variant()) {
-      case 2: launch_pair<16, 6>(ctx, g, ah, al, bh, bl, a_mn, b_mn); break;
-      case 3: launch_pair<16, 4>(ctx, g, ah, al, bh, bl, a_mn, b_mn); break;
-      default: launch_pair<32, 3>(ctx, g, ah, al, bh, bl, a_mn, b_mn); break;
+      case 2: launch_pair<16, 6>(ctx, g, ah, al, bh, bl, a_mn, b_mn, lda, ldb); break;
+      case 3: launch_pair<16, 4>(ctx, g, ah, al, bh, bl, a_mn, b_mn, lda, ldb); break;
+      default: launch_pair<32, 3>(ctx, g, ah, al, bh, bl, a_mn, b_mn, lda, ldb); break;
     }
   } else {
     if (g.push) fail(GADCU_ERR_UNSUPPORTED, "gemm: the tile-pushing epilogue needs M and N to be multiples of 256");

@@ -60,3 +60,51 @@ def test_gemm_tc_accumulate_epilogue(ctx):
     want = 2.0 * (x.astype(np.float64).T @ seed.astype(np.float64))
     bound = 2.0 ** -19 * (np.abs(x.astype(np.float64)).T @ np.abs(seed.astype(np.float64)))
     assert np.all(np.abs(got - want) <= bound)
+
+
+# ---- shapes that are not multiples of the tile: zero-filled edge tiles, predicated epilogue -----------------------
+@pytest.mark.parametrize("t1,t2", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(1000, 1000, 1000), (300, 4100, 777), (4097, 100, 333), (77, 5000, 99), (257, 513, 4099)])
+def test_gemm_tc_ragged_shapes_match_f64(ctx, M, N, K, t1, t2):
+    launches = ctx.launches()
+    _check(ctx, M, N, K, t1, t2, seed=M + K)
+    assert ctx.launches() - launches == 3  # two operand splits + ONE tensor-core GEMM (no CUDA-core fallback pieces)
+
+
+def test_gemm_tc_ragged_is_exact_on_small_integers(ctx):
+    """Integer-valued operands: every partial product and sum is exact in TF32 x TF32 -> f32, so any element that
+    came from the wrong place (edge tile, padded column, k tail) shows as a whole-number error."""
+    rng = np.random.default_rng(5)
+    ev = gb.Eval(ctx)
+    for (M, N, K) in [(999, 1001, 515), (2049, 260, 1030), (70, 70, 3500)]:
+        for t1 in (False, True):
+            for t2 in (False, True):
+                sa, sb = ((K, M) if t1 else (M, K)), ((N, K) if t2 else (K, N))
+                a = rng.integers(-4, 5, sa).astype(np.float32)
+                b = rng.integers(-4, 5, sb).astype(np.float32)
+                got = to_np(ev.matmul(ev.constant(a), ev.constant(b), gb.MatProp(t1), gb.MatProp(t2)))[:, :, 0, 0]
+                want = (a.T if t1 else a).astype(np.float64) @ (b.T if t2 else b).astype(np.float64)
+                assert got.shape == (M, N)
+                assert np.array_equal(got.astype(np.float64), want), (M, N, K, t1, t2)
+
+
+def test_gemm_tc_ragged_mlp_gradients(ctx):
+    """A tanh layer with batch 1000 and widths 520 -> 392: forward, dA and dW all ragged; dW accumulates (w used
+    twice); gradients against f64."""
+    rng = np.random.default_rng(9)
+    B, D, H = 1000, 520, 392
+    x = rng.standard_normal((B, D)).astype(np.float32)
+    w = (rng.standard_normal((D, H)) / np.sqrt(D)).astype(np.float32)
+    g = gb.Graph1(ctx)
+    vx, vw = g.variable(x), g.variable(w)
+    y = g.add(g.tanh(g.matmul_nn(vx, vw)), g.matmul_nn(vx, vw))
+    loss = g.norm2(y)
+    store = g.evaluate_gradients_once(loss.gid(), 1.0)
+    X, W = x.astype(np.float64), w.astype(np.float64)
+    Z = X @ W
+    Y = np.tanh(Z) + Z
+    dZ = 2 * Y * (1 - np.tanh(Z) ** 2) + 2 * Y
+    for got, want in [(store.get(vw.gid()), X.T @ dZ), (store.get(vx.gid()), dZ @ W.T)]:
+        got = to_np(got)[:, :, 0, 0].astype(np.float64)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
