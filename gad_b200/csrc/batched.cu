@@ -81,6 +81,8 @@ struct SymProgram {
     std::vector<uint64_t> tile_d0;
     std::vector<double> imms;
     int V = 1, U = 1, block = 128;
+    size_t smem_bytes = 0;  // > 0: the staged kernel (persistent blocks of block + 32 threads, see JitPlan::ring)
+    int stage_blocks = 0;
     uint64_t instructions = 0, values = 0;
   };
   std::map<std::vector<int32_t>, Compiled> compiled;
@@ -260,6 +262,11 @@ void launch_interpreter(gadcu_ctx* ctx, int slots, const DevInstr* prog, int n, 
 // Kernel parameters may be up to 32 764 bytes on sm_70+ (CUDA 12.1+); one pointer per input / output column, one
 // double per constant. Requests with more outputs than fit are computed in several kernels.
 constexpr size_t kMaxParamBytes = 32000;
+// persistent blocks of a staged lane program: as many as fit an SM by shared memory (227 KB), on every SM
+uint64_t staged_grid(gadcu_ctx* ctx, size_t smem_bytes, int blocks_per_sm) {
+  const uint64_t fit = std::max<uint64_t>(1, (227 * 1024) / (smem_bytes + 1024));
+  return uint64_t(ctx->sm_count) * std::min<uint64_t>(fit, uint64_t(blocks_per_sm));
+}
 constexpr size_t kMaxOutputsPerKernel = 1024;
 
 bool use_jit() {
@@ -468,6 +475,12 @@ struct JitPlan {
   // enough resident warps to stream from HBM. Any order that respects the data flow gives the same bits.
   bool flat = false;
   std::vector<int32_t> sched;
+  // flat + ring > 0: the lane inputs are not loaded by the computing threads but streamed into a shared-memory ring of
+  // `ring` column tiles by a producer warp (cp.async.bulk + mbarriers), which runs ahead across tiles: the bytes in
+  // flight no longer cost registers (the register-prefetching kernel was pinned at 8 resident warps by its ~200
+  // registers and at 8 loads in flight per thread by the same budget)
+  int ring = 0, stage_blocks = 0;  // ring depth; resident blocks per SM the kernel is compiled for (its register budget)
+  size_t smem_bytes = 0;
 };
 
 thread_local const JitPlan* g_plan = nullptr;  // the plan being rendered by this thread
@@ -506,15 +519,68 @@ std::string gen_source(const SymProgram& P, const JitPlan& J, const std::unorder
     const char* sfx[2] = {W == 1 ? "" : "_0", "_1"};
     const char* comp[2] = {".x", ".y"};
     o << "typedef " << (f32 ? "float2" : "double2") << " TV2;\n";
+    std::unordered_map<int32_t, int> ring_index;  // lane load -> its position among the tile's loads, in schedule order
+    if (J.ring) {
+      const int stage_blocks = J.stage_blocks;
+      std::vector<int> table;
+      for (int32_t r : J.sched)
+        if (P.cache.count(r) || P.instrs[r].op == S_LOAD) {
+          ring_index[r] = int(table.size());
+          table.push_back(in_slot.at(r));
+        }
+      const int D = J.ring, NL = int(table.size());
+      int logd = 0;
+      while ((1 << logd) < D) logd++;
+      o << "#define TILE_BYTES " << J.block * W * (f32 ? 4 : 8) << "u\n";
+      o << "__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {\n  unsigned done;\n  do {\n"
+           "    asm volatile(\"{\\n.reg .pred p;\\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\\nselp.u32 %0, 1, 0, p;\\n}\" : \"=r\"(done) : \"r\"(bar), \"r\"(parity) : \"memory\");\n"
+           "  } while (!done);\n}\n";
+      o << "__constant__ unsigned short ring_slot_of[" << NL << "] = {";
+      for (int j = 0; j < NL; j++) o << table[size_t(j)] << (j + 1 < NL ? "," : "");
+      o << "};\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(" << J.block + 32 << ", " << stage_blocks << ") lane_program(const P p) {\n";
+      o << "  extern __shared__ __align__(128) unsigned char smem[];\n";
+      o << "  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem), bfull = sbase + " << D << "u * TILE_BYTES, bempty = bfull + " << 8 * D << "u;\n";
+      o << "  if (threadIdx.x == 0) {\n    for (unsigned s = 0; s < " << D << "u; s++) {\n"
+           "      asm volatile(\"mbarrier.init.shared::cta.b64 [%0], %1;\" ::\"r\"(bfull + 8 * s), \"r\"(1u));\n"
+           "      asm volatile(\"mbarrier.init.shared::cta.b64 [%0], %1;\" ::\"r\"(bempty + 8 * s), \"r\"(" << J.block / 32 << "u));\n    }\n"
+           "    asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n"
+           "    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n  }\n  __syncthreads();\n";
+      o << "  const u64 units = p.n / " << W << ";\n  const u64 tiles = (units + " << J.block - 1 << "ull) / " << J.block << "ull;\n";
+      o << "  if (threadIdx.x >= " << J.block << ") {\n    if (threadIdx.x == " << J.block << ") {\n      unsigned q = 0;\n"
+           "      for (u64 t = blockIdx.x; t < tiles; t += gridDim.x) {\n"
+           "        const u64 first = t * " << J.block << "ull;\n        const u64 left = units - first;\n"
+           "        const unsigned bytes = (unsigned)(left < " << J.block << "ull ? left : " << J.block << "ull) * " << W * (f32 ? 4 : 8) << "u;\n"
+           "#pragma unroll 1\n        for (int j = 0; j < " << NL << "; j++, q++) {\n"
+           "          const unsigned s = q & " << D - 1 << "u, ph = (q >> " << logd << ") & 1u;\n"
+           "          mbar_wait(bempty + 8 * s, ph ^ 1u);\n"
+           "          asm volatile(\"mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\" ::\"r\"(bfull + 8 * s), \"r\"(bytes) : \"memory\");\n"
+           "          asm volatile(\"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\" ::\"r\"(sbase + s * TILE_BYTES), "
+           "\"l\"(p.in[ring_slot_of[j]] + first * " << W << "ull), \"r\"(bytes), \"r\"(bfull + 8 * s) : \"memory\");\n"
+           "        }\n      }\n    }\n    return;\n  }\n";
+      o << "  unsigned q0 = 0;\n  for (u64 t = blockIdx.x; t < tiles; t += gridDim.x, q0 += " << NL << "u) {\n"
+           "    const u64 i = t * " << J.block << "ull + threadIdx.x;\n    const bool live = i < units;\n";
+    } else {
     o << "extern \"C\" __global__ void __launch_bounds__(" << J.block;
     if (min_blocks > 0) o << ", " << (W == 1 ? min_blocks : std::max(1, min_blocks / 3));  // two lanes: 2 x 128 threads, ~200 registers, no spills
     o << ") lane_program(const P p) {\n";
     o << "  const u64 tid = (u64)blockIdx.x * " << J.block << "ull + threadIdx.x;\n  const u64 stride = (u64)gridDim.x * " << J.block << "ull;\n";
     o << "  for (u64 i = tid; i < p.n / " << W << "; i += stride) {\n";
+    }
     for (int32_t r : J.sched) {
       const SymInstr& I = P.instrs[r];
       const bool cached = P.cache.count(r) != 0;
-      if (cached || I.op == S_LOAD) {
+      if ((cached || I.op == S_LOAD) && J.ring) {
+        int logd = 0;
+        while ((1 << logd) < J.ring) logd++;
+        const int j = ring_index.at(r);
+        o << "    TV2 v" << reg_name(r) << ";\n    {\n      const unsigned q = q0 + " << j << "u, s = q & " << J.ring - 1 << "u;\n"
+             "      mbar_wait(bfull + 8 * s, (q >> " << logd << ") & 1u);\n"
+             "      v" << reg_name(r) << " = *reinterpret_cast<const TV2*>(smem + s * TILE_BYTES + threadIdx.x * sizeof(TV2));\n"
+             "      __syncwarp();\n"
+             "      if ((threadIdx.x & 31) == 0) asm volatile(\"mbarrier.arrive.shared::cta.b64 _, [%0];\" ::\"r\"(bempty + 8 * s) : \"memory\");\n    }\n";
+        for (int l = 0; l < W; l++) o << "    const T " << reg_name(r) << sfx[l] << " = v" << reg_name(r) << comp[l] << ";\n";
+      } else if (cached || I.op == S_LOAD) {
         if (W == 1) {
           o << "    const T " << reg_name(r) << " = __ldcs(p.in[" << in_slot.at(r) << "] + i);\n";
         } else {
@@ -553,8 +619,8 @@ std::string gen_source(const SymProgram& P, const JitPlan& J, const std::unorder
         if (W == 1) {
           o << "    p.out[" << os->second << "][i] = " << reg_name(r) << ";\n";
         } else {
-          o << "    { TV2 w; w.x = " << reg_name(r) << sfx[0] << "; w.y = " << reg_name(r) << sfx[1] << "; reinterpret_cast<TV2*>(p.out[" << os->second
-            << "])[i] = w; }\n";
+          o << "    " << (J.ring ? "if (live) " : "") << "{ TV2 w; w.x = " << reg_name(r) << sfx[0] << "; w.y = " << reg_name(r) << sfx[1]
+            << "; reinterpret_cast<TV2*>(p.out[" << os->second << "])[i] = w; }\n";
         }
       }
     }
@@ -662,11 +728,12 @@ std::vector<ArrayRef> SymProgram::launch_compiled(const Compiled& c, size_t nout
   uint64_t grid = (lanes + per_block - 1) / per_block;
   const uint64_t cap = uint64_t(ctx->sm_count) * (c.block == 256 ? 8 : 16);
   if (grid > cap && c.V > 1) grid = cap;
+  if (c.smem_bytes) grid = std::min<uint64_t>(grid, staged_grid(ctx, c.smem_bytes, c.stage_blocks));
   if (grid > 0x7fffffffull) grid = 0x7fffffffull;
   if (grid == 0) grid = 1;
   ProfileScope prof_scope(ctx, array_mode ? PROF_EW : PROF_OTHER);
   void* args[] = {params.data()};
-  jit::launch(ctx, c.kernel, unsigned(grid), unsigned(c.block), args);
+  jit::launch(ctx, c.kernel, unsigned(grid), unsigned(c.block + (c.smem_bytes ? 32 : 0)), args, c.smem_bytes);
   last_instructions = c.instructions;
   last_slots = c.values;
   return out_cols;
@@ -829,7 +896,21 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
       ready.pop_back();
       place(r);
     }
-    {  // software pipelining of the lane loads: the load that was about to be used is replaced, in place, by the load
+    {  // shared-memory staging of the lane inputs (see JitPlan::ring): two lanes per thread, whole 16-byte units
+      static const int stage = [] { const char* e = getenv("GADCU_LANE_STAGE"); return e ? atoi(e) : 8; }();  // C2: 8 tiles x 5 blocks 0.184 ms, 32 x 3 0.187, 32 x 2 0.199, registers only 0.196
+      size_t lane_loads = 0;
+      bool aligned = true;
+      for (int32_t r : J.sched)
+        if (cache.count(r) || instrs[r].op == S_LOAD) lane_loads++;
+      for (auto& d : J.dense) aligned = aligned && (reinterpret_cast<uintptr_t>(J.in_ptrs[size_t(d.second)]) & 15) == 0;
+      if (stage > 0 && J.V == 2 && lane_loads >= 8 && aligned && lanes % 4 == 0) {
+        int D = 1;
+        while (D * 2 <= stage && size_t(D * 2) <= lane_loads) D *= 2;
+        J.ring = D;
+        J.smem_bytes = size_t(D) * size_t(J.block) * 2 * (dtype == GADCU_F32 ? 4 : 8) + size_t(D) * 16;
+      }
+    }
+    if (!J.ring) {  // software pipelining of the lane loads: the load that was about to be used is replaced, in place, by the load
        // needed kPrefetch loads later, and the first kPrefetch are issued up front — every warp keeps kPrefetch
        // independent 256-byte requests in flight (one in flight per warp cannot cover HBM latency at any occupancy)
       static const size_t kPrefetch = [] { const char* e = getenv("GADCU_LANE_PREFETCH"); return e ? size_t(atoi(e)) : size_t(8); }();
@@ -867,7 +948,7 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   std::string key;
   key.reserve(J.order.size() * 24 + 64);
   key += dtype == GADCU_F32 ? "f32" : "f64";
-  key += "|V" + std::to_string(J.V) + "U" + std::to_string(J.U) + "B" + std::to_string(J.block) + (J.idx32 ? "i32" : "i64") + (J.flat ? "flat" : "");
+  key += "|V" + std::to_string(J.V) + "U" + std::to_string(J.U) + "B" + std::to_string(J.block) + (J.idx32 ? "i32" : "i64") + (J.flat ? "flat" : "") + (J.ring ? "ring" + std::to_string(J.ring) : "");
   auto L = [&](int32_t r) { return r < 0 ? std::string("-") : std::to_string(J.local.at(r)); };
   auto list = [&](const char* tag, const std::vector<std::pair<int32_t, int>>& v) {
     key += tag;
@@ -884,16 +965,43 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
     const SymInstr& I = instrs[r];
     key += L(r) + ":" + std::to_string(I.op) + "(" + L(I.a) + "," + L(I.b) + "," + L(I.c) + "," + L(I.d) + ");";
   }
-  const jit::Kernel* kernel = jit::find(key);
-  if (!kernel) {
-    g_plan = &J;
-    const std::string src = gen_source(*this, J, imm_slot);
-    g_plan = nullptr;
-    if (const char* dump = getenv("GADCU_JIT_DUMP")) {
-      FILE* f = fopen(dump, "a");
-      if (f) { fprintf(f, "// ---- key %zu bytes, %zu instructions\n%s\n", key.size(), J.order.size(), src.c_str()); fclose(f); }
+  auto build = [&](const std::string& k) {
+    const jit::Kernel* kernel = jit::find(k);
+    if (!kernel) {
+      g_plan = &J;
+      const std::string src = gen_source(*this, J, imm_slot);
+      g_plan = nullptr;
+      if (const char* dump = getenv("GADCU_JIT_DUMP")) {
+        FILE* f = fopen(dump, "a");
+        if (f) { fprintf(f, "// ---- key %zu bytes, %zu instructions\n%s\n", k.size(), J.order.size(), src.c_str()); fclose(f); }
+      }
+      kernel = jit::compile(k, src, "lane_program");
     }
-    kernel = jit::compile(key, src, "lane_program");
+    return kernel;
+  };
+  const jit::Kernel* kernel = nullptr;
+  if (J.ring) {
+    // the staged kernel is compiled for as many resident blocks per SM as its registers allow without spilling:
+    // 5 (<= 80 registers), else 3 (<= 136), else 2; the choice is remembered per structure
+    static std::mutex chosen_mu;
+    static std::unordered_map<std::string, int> chosen;
+    static const int forced = [] { const char* e = getenv("GADCU_LANE_STAGE_BLOCKS"); return e ? atoi(e) : 0; }();
+    int known = 0;
+    {
+      std::lock_guard<std::mutex> lk(chosen_mu);
+      auto it = chosen.find(key);
+      if (it != chosen.end()) known = it->second;
+    }
+    const std::vector<int> candidates = known ? std::vector<int>{known} : forced > 0 ? std::vector<int>{forced} : std::vector<int>{5, 3, 2};
+    for (size_t c = 0; c < candidates.size(); c++) {
+      J.stage_blocks = candidates[c];
+      kernel = build(key + "|b" + std::to_string(J.stage_blocks));
+      if (kernel->local_bytes == 0 || c + 1 == candidates.size()) break;
+    }
+    std::lock_guard<std::mutex> lk(chosen_mu);
+    chosen[key] = J.stage_blocks;
+  } else {
+    kernel = build(key);
   }
   if (reusable && J.imms.size() * 8 + (J.in_ptrs.size() + J.outs.size() + J.tile_d0.size() + 1) * 8 <= kMaxParamBytes) {
     Compiled c;
@@ -902,6 +1010,8 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
     c.tile_d0 = J.tile_d0;
     c.imms = J.imms;
     c.V = J.V; c.U = J.U; c.block = J.block;
+    c.smem_bytes = J.smem_bytes;
+    c.stage_blocks = J.stage_blocks;
     c.instructions = last_instructions;
     c.values = last_slots;
     compiled[todo] = std::move(c);
@@ -922,12 +1032,13 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   uint64_t grid = (lanes + per_block - 1) / per_block;
   const uint64_t cap = uint64_t(ctx->sm_count) * (J.block == 256 ? 8 : 16);
   if (grid > cap && J.V > 1) grid = cap;          // grid-stride for the streaming kernels
+  if (J.ring) grid = std::min<uint64_t>(grid, staged_grid(ctx, J.smem_bytes, J.stage_blocks));
   if (grid > 0x7fffffffull) grid = 0x7fffffffull;
   if (grid == 0) grid = 1;
   {
     ProfileScope prof_scope(ctx, array_mode ? PROF_EW : PROF_OTHER);
     void* args[] = {params.data()};
-    jit::launch(ctx, kernel, unsigned(grid), unsigned(J.block), args);
+    jit::launch(ctx, kernel, unsigned(grid), unsigned(J.block + (J.ring ? 32 : 0)), args, J.smem_bytes);
   }
   return out_cols;
 }

@@ -107,9 +107,10 @@ const Kernel* compile(const std::string& key, const std::string& source, const c
   Kernel k;
   GADCU_CUDA(cudaLibraryLoadData(&k.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   GADCU_CUDA(cudaLibraryGetKernel(&k.fn, k.lib, entry));
-  if (const char* dump = getenv("GADCU_JIT_DUMP")) {
-    cudaFuncAttributes attr;
-    if (cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(k.fn)) == cudaSuccess) {
+  cudaFuncAttributes attr;
+  if (cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(k.fn)) == cudaSuccess) {
+    k.local_bytes = attr.localSizeBytes;
+    if (const char* dump = getenv("GADCU_JIT_DUMP")) {
       if (FILE* f = fopen(dump, "a")) {
         fprintf(f, "// compiled: %d registers, %zu bytes local (spills), %zu bytes cubin\n", attr.numRegs, attr.localSizeBytes, cubin.size());
         fclose(f);
@@ -122,8 +123,12 @@ const Kernel* compile(const std::string& key, const std::string& source, const c
   return &res.first->second;
 }
 
-void launch(gadcu_ctx* ctx, const Kernel* k, unsigned grid, unsigned block, void** args) {
-  GADCU_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k->fn), dim3(grid), dim3(block), args, 0, ctx->stream));
+void launch(gadcu_ctx* ctx, const Kernel* k, unsigned grid, unsigned block, void** args, size_t smem_bytes) {
+  if (smem_bytes > k->smem_allowed) {
+    GADCU_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(k->fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+    k->smem_allowed = smem_bytes;
+  }
+  GADCU_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k->fn), dim3(grid), dim3(block), args, smem_bytes, ctx->stream));
   ctx->count_launch();
 }
 

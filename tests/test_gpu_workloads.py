@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 # ---- C1 / C2: scalar tapes, one per lane ------------------------------------------------------------
-@pytest.mark.parametrize("n,lanes", [(2, 1), (8, 33), (64, 1000), (64, 4097)])
+@pytest.mark.parametrize("n,lanes", [(2, 1), (8, 33), (64, 1000), (64, 4097), (64, 256 * 148 * 5 + 8), (40, 4)])
 def test_batched_rosenbrock_matches_scalar_tape_bit_for_bit(ctx, oracle, n, lanes):
     """Rosenbrock uses only +, -, *, neg and constants: every op is an exactly rounded IEEE operation,
     the op order is the tape's, no FMA contraction on either side => f64 results are bit-identical to
@@ -85,6 +85,32 @@ def test_batched_tape_golden_point_and_f32(ctx):
              "tanh": 1 - np.tanh(x64) ** 2, "sigmoid": np.exp(-x64) / (1 + np.exp(-x64)) ** 2, "reciprocal": -1 / x64 ** 2,
              "sqrt": 0.5 / np.sqrt(x64)}[name] * 2 * 1.7
         assert np.allclose(got, d, rtol=2e-5, atol=1e-6), name
+
+
+def test_staged_lane_program_f32_f64_partial_tiles(ctx):
+    """Long tapes stream their input columns through a shared-memory ring fed by cp.async.bulk (batched.cu, JitPlan::ring):
+    f64 and f32, whole and partial last tiles, against the tape's reverse sweep restated in numpy (the f64 bit-for-bit
+    comparison with the scalar oracle tape is test_batched_rosenbrock_matches_scalar_tape_bit_for_bit, whose 1000-,
+    4-lane and 189 448-lane cases run through this kernel too); a re-run gives the same bits."""
+    for dtype, npdt, lanes in [(gb.F64, np.float64, 2000), (gb.F32, np.float32, 1004), (gb.F32, np.float32, 128 * 2 * 3)]:
+        n = 48
+        x = (-1.2 + 2.4 * np.random.default_rng(lanes).random((n, lanes))).astype(npdt)
+        cols = [ctx.array(x[i]) for i in range(n)]
+        _, f, grads, store = wl.rosenbrock_batched_gradients(ctx, cols, dtype)
+        got = np.stack([to_np(c)[:, 0, 0, 0] for c in grads])
+        assert got.dtype == npdt
+        # the same tape, one lane at a time through numpy in the tape's operation order
+        gx = np.zeros_like(x)
+        for i in range(n - 1):
+            sq = x[i] * x[i]; d = x[i + 1] - sq; e = -x[i] + npdt(1)
+            # forward: t1 = 100 d^2, e2 = e^2; reverse (seed 1): see SURVEY App. D
+            gd = (npdt(1) * npdt(100)) * d + (npdt(1) * npdt(100)) * d   # d2 = d*d: both operand contributions
+            ge = e + e
+            gx[i + 1] += gd
+            gx[i] += -(gd * x[i] + gd * x[i]) - ge
+        assert np.allclose(got, gx, rtol=2e-4 if npdt == np.float32 else 1e-12, atol=1e-3 if npdt == np.float32 else 1e-9)
+        again = store.rerun(cols)
+        assert np.array_equal(np.stack([to_np(c)[:, 0, 0, 0] for c in again]), got)
 
 
 def test_batched_select_pow_div_vs_scalar_oracle(ctx, oracle):
