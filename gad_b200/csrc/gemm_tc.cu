@@ -834,7 +834,10 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   if (streamk && tiles % clusters != 0) {
     const uint64_t rem = tiles % clusters, helpers = clusters - rem, per_helper = (rem + helpers - 1) / helpers;
     const uint64_t tail = kb_per_tile / (per_helper + 1);  // head (KB - tail) = per_helper tails
-    if (tail >= min_tail) sk.rem = uint32_t(rem), sk.tail_kb = uint32_t(tail);  // (shorter tails: the epilogues would dominate)
+    // worth it when it shortens the launch by 3 % or more: 512 tiles (6.92 waves: 1 % to gain) measured 5 % SLOWER split
+    // than whole — twelve 9-block tails per helper are epilogue-bound and the heads' read-add-store epilogue is exposed
+    const double gain = double(tail) / double((tiles / clusters + 1) * kb_per_tile);
+    if (tail >= min_tail && gain >= 0.03) sk.rem = uint32_t(rem), sk.tail_kb = uint32_t(tail);
   }
   static const int trace_at = [] { const char* e = getenv("GADCU_SK_TRACE"); return e ? atoi(e) : 0; }();  // trace the n-th launch
   static int trace_count = 0;
