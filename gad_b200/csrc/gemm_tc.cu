@@ -837,7 +837,11 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
     // worth it when it shortens the launch by 3 % or more: 512 tiles (6.92 waves: 1 % to gain) measured 5 % SLOWER split
     // than whole — twelve 9-block tails per helper are epilogue-bound and the heads' read-add-store epilogue is exposed
     const double gain = double(tail) / double((tiles / clusters + 1) * kb_per_tile);
-    if (tail >= min_tail && gain >= 0.03) sk.rem = uint32_t(rem), sk.tail_kb = uint32_t(tail);
+    // ... and not for a single partial wave that already covers most of the chip (64 tiles on 74 clusters, the 1024-row
+    // shards of an 8-GPU step): no gain alone (0.132 ms either way: the idle SMs' power goes to the busy ones) and 2.5 %
+    // slower inside the 8-GPU step (516 vs 503 steps/s), where the idle SMs are what the exchange kernels run on
+    const bool lone_wide_wave = tiles < clusters && tiles * 2 > clusters;
+    if (tail >= min_tail && gain >= 0.03 && !lone_wide_wave) sk.rem = uint32_t(rem), sk.tail_kb = uint32_t(tail);
   }
   static const int trace_at = [] { const char* e = getenv("GADCU_SK_TRACE"); return e ? atoi(e) : 0; }();  // trace the n-th launch
   static int trace_count = 0;
