@@ -149,6 +149,32 @@ def cpu_mlp_steps_per_s(rows: int, threads: int, repeats: int = 1):
     return 1.0 / (best * (B_TOTAL / rows)), best
 
 
+def cpu_secondary(threads: int):
+    """The restated CPU path beside the secondary metrics, each on a bounded sample (about a second of CPU work):
+    C1 one scalar Rosenbrock-64 tape on one core, C2 the same tape looped over lanes on all cores, C3 the HostArray tape
+    (one core: the reference's CPU arrays are single-threaded per op) with the reverse sweep timed on its own."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py
+    rng = np.random.default_rng(2)
+    out = {}
+    x1 = -1.2 + 2.4 * rng.random((64, 1024))
+    _, _, secs = oracle_py.rosenbrock_batch(x1, nthreads=1)
+    out["c1"] = {"value": x1.shape[1] / secs, "unit": "grads/s", "cores": 1, "kind": "port",
+                 "sample": "1024 Rosenbrock-64 f64 scalar Graph1 tapes, recorded and swept one after the other"}
+    lanes = 2048 * threads
+    xs = -1.2 + 2.4 * rng.random((64, lanes))
+    _, _, secs = oracle_py.rosenbrock_batch(xs, nthreads=threads)
+    out["c2"] = {"value": lanes / secs, "unit": "grads/s", "cores": threads, "kind": "port",
+                 "sample": f"{lanes} of 1048576 lanes (the scalar tape looped over lanes, {threads} threads); grads/s needs no scaling"}
+    n = 1 << 22
+    x = rng.uniform(-1.0, 1.0, n).astype(np.float32)
+    y = rng.uniform(0.5, 2.0, n).astype(np.float32)
+    _, _, _, secs, sweep = oracle_py.c3(x, y)
+    out["c3"] = {"value": 16.0 * n / sweep / 1e9, "unit": "GB/s", "cores": 1, "kind": "port", "fwd_plus_sweep_seconds": secs,
+                 "sample": f"n = {n} of 67108864 elements (HostArray tape, per-node sweep); algorithmic GB/s = 16 B/element / sweep time, size-independent"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -441,6 +467,15 @@ def secondary_metrics(ctx, ext, torch, gb, wl, pk, args):
     del cols, res
 
     out["hvp"] = hvp_metric(ctx, ext, torch, wl, None, 1, 0)
+    try:  # the CPU port beside each number (rank 0, one GPU only: this function runs there)
+        cpu = cpu_secondary(host_cores())
+        out["grad_sweep"]["cpu_baseline"] = cpu["c3"]
+        out["batched_tape"]["cpu_baseline"] = cpu["c2"]
+        out["scalar_tape"] = {"metric": "scalar-tape grads/s", "workload": "C1 one Rosenbrock-64 f64 Graph1 tape at a time (CPU only: "
+                              "the device result for a single tape is a parity check, tests/test_gpu_workloads.py, not a throughput claim)",
+                              "cpu_baseline": cpu["c1"]}
+    except Exception as e:  # (never lose the bench line over a baseline)
+        out["cpu_baseline_error"] = repr(e)
     return out
 
 
