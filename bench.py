@@ -467,6 +467,10 @@ def secondary_metrics(ctx, ext, torch, gb, wl, pk, args):
     del cols, res
 
     out["hvp"] = hvp_metric(ctx, ext, torch, wl, None, 1, 0)
+    try:  # launch-bound sizes: the same step eager and as ONE replayed CUDA graph (gadcu_capture_*, north-star subsystem 1)
+        out["graph_replay"] = replay_metric(ctx, ext, torch, gb, wl)
+    except Exception as e:
+        out["graph_replay"] = {"error": repr(e)}
     try:  # the CPU port beside each number (rank 0, one GPU only: this function runs there)
         cpu = cpu_secondary(host_cores())
         out["grad_sweep"]["cpu_baseline"] = cpu["c3"]
@@ -477,6 +481,63 @@ def secondary_metrics(ctx, ext, torch, gb, wl, pk, args):
     except Exception as e:  # (never lose the bench line over a baseline)
         out["cpu_baseline_error"] = repr(e)
     return out
+
+
+def replay_metric(ctx, ext, torch, gb, wl):
+    """Where launch overhead, not the GPU, bounds a step: a small C4-shaped MLP step (B=512, D=256: 29 launches of a few
+    microseconds each) and the C3 tape at n = 2^16, issued eagerly through the API and replayed as one captured graph.
+    Device time per step with CUDA events on the context's stream, 200 steps after warm-up."""
+    def ev_time(fn, reps):
+        ctx.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(reps):
+            fn()
+        e1.record(ext)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    res = {}
+    B_, D_ = 512, 256
+    X = ctx.random((B_, D_), 5, normal=True, a=0.0, b=1.0)
+    T = ctx.random((B_, D_), 9, normal=True, a=0.0, b=1.0)
+    Ws = [ctx.random((D_, D_), 6 + l, normal=True, a=0.0, b=1.0 / np.sqrt(D_)) for l in range(L)]
+    bs = [ctx.array(np.full((1, D_), 0.01, np.float32)) for _ in range(L)]
+    keep = {}
+
+    def eager():
+        keep["e"] = wl.mlp_step(ctx, X, Ws, bs, T)
+
+    for _ in range(5):
+        eager()
+    ms_eager = ev_time(eager, 200)
+    with gb.Capture(ctx) as cap:
+        captured = wl.mlp_step(ctx, X, Ws, bs, T)
+    for _ in range(5):
+        cap.launch()
+    ms_replay = ev_time(cap.launch, 200)
+    same = captured[0].item() == keep["e"][0].item()
+    res["mlp_small"] = {"workload": f"C4-shaped step at B={B_}, D={D_}, L={L}, f32", "eager_ms": ms_eager, "replay_ms": ms_replay,
+                        "eager_steps_per_s": 1e3 / ms_eager, "replay_steps_per_s": 1e3 / ms_replay, "loss_identical": bool(same)}
+    del cap, captured
+    n = 1 << 16
+    x = ctx.random((n,), 3, a=-1.0, b=1.0)
+    y = ctx.random((n,), 4, a=0.5, b=2.0)
+
+    def eager3():
+        keep["c3"] = wl.c3_step(ctx, x, y)
+
+    for _ in range(5):
+        eager3()
+    ms_eager3 = ev_time(eager3, 200)
+    with gb.Capture(ctx) as cap3:
+        captured3 = wl.c3_step(ctx, x, y)
+    for _ in range(5):
+        cap3.launch()
+    ms_replay3 = ev_time(cap3.launch, 200)
+    res["c3_small"] = {"workload": f"C3 tape at n={n}, f32, forward + reverse sweep", "eager_ms": ms_eager3, "replay_ms": ms_replay3,
+                       "z_identical": bool(captured3[0].item() == keep["c3"][0].item())}
+    return res
 
 
 def hvp_metric(ctx, ext, torch, wl, comm, world, rank, dist=None):
