@@ -15,12 +15,19 @@ pub const GADCU_ERR_EMPTY: gadcu_status = 4;
 pub const GADCU_ERR_MISSING_ID: gadcu_status = 5;
 pub const GADCU_ERR_MISSING_GRADIENT: gadcu_status = 6;
 pub const GADCU_ERR_MISSING_NODE: gadcu_status = 7;
+// new with this backend
+pub const GADCU_ERR_CUDA: gadcu_status = 8;
+pub const GADCU_ERR_NCCL: gadcu_status = 9;
+pub const GADCU_ERR_UNSUPPORTED: gadcu_status = 10;
+pub const GADCU_ERR_INVALID: gadcu_status = 11;
+pub const GADCU_ERR_TYPE: gadcu_status = 12;
 
 #[repr(C)] pub struct gadcu_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct gadcu_array { _p: [u8; 0] }
 #[repr(C)] pub struct gadcu_algebra { _p: [u8; 0] }
 #[repr(C)] pub struct gadcu_store { _p: [u8; 0] }
 #[repr(C)] pub struct gadcu_comm { _p: [u8; 0] }
+#[repr(C)] pub struct gadcu_capture { _p: [u8; 0] }
 
 #[repr(C)] #[derive(Clone, Copy, PartialEq, Eq, Debug)]
 pub struct gadcu_dim4 { pub d: [u64; 4] }
@@ -41,6 +48,9 @@ type A = *mut gadcu_algebra;
 type V = *const gadcu_value;
 type O = *mut gadcu_value;
 type D = *const gadcu_dim4;
+/// VJP of a user-defined node (gad/src/graph.rs:106-165; tests/extension.rs:61-96): gets the gradient algebra
+/// (Eval for Graph1, the graph itself for GraphN), the store and the node's own gradient.
+pub type gadcu_vjp_fn = unsafe extern "C" fn(user: *mut c_void, grad_algebra: A, store: *mut gadcu_store, gradient: V) -> gadcu_status;
 
 extern "C" {
     pub fn gadcu_last_error() -> *const c_char;
@@ -129,4 +139,62 @@ extern "C" {
     pub fn gadcu_comm_init(ctx: *mut gadcu_ctx, nranks: c_int, rank: c_int, id: *const c_void, out: *mut *mut gadcu_comm) -> gadcu_status;
     pub fn gadcu_comm_allreduce_sum(comm: *mut gadcu_comm, arrays: *const *mut gadcu_array, n: usize) -> gadcu_status;
     pub fn gadcu_comm_destroy(comm: *mut gadcu_comm) -> gadcu_status;
+}
+
+// ---- the rest of include/gadcu.h: helpers of the derived trait methods, user nodes, and the entry points that have no
+// counterpart in the reference (tests/test_check_and_abi.py keeps this file and the header in step)
+extern "C" {
+    pub fn gadcu_version() -> *const c_char;
+    pub fn gadcu_ctx_stream(ctx: *mut gadcu_ctx) -> *mut c_void;
+    pub fn gadcu_ctx_set_fusion(ctx: *mut gadcu_ctx, fuse: c_int) -> gadcu_status;
+    pub fn gadcu_ctx_set_lazy(ctx: *mut gadcu_ctx, enable: c_int, min_elements: u64) -> gadcu_status;
+    pub fn gadcu_ctx_set_strict_reference(ctx: *mut gadcu_ctx, strict: c_int) -> gadcu_status;
+    pub fn gadcu_ctx_memory_stats(ctx: *mut gadcu_ctx, bytes_in_use: *mut u64, bytes_reserved: *mut u64, kernel_launches: *mut u64) -> gadcu_status;
+    pub fn gadcu_ctx_profile_begin(ctx: *mut gadcu_ctx) -> gadcu_status;
+    pub fn gadcu_ctx_profile_end(ctx: *mut gadcu_ctx, ms_by_category4: *mut f64, count_by_category4: *mut u64) -> gadcu_status;
+    pub fn gadcu_ctx_wait_uploads(ctx: *mut gadcu_ctx) -> gadcu_status;
+    // arrays
+    pub fn gadcu_array_alloc(ctx: *mut gadcu_ctx, dt: c_int, dims: D, out: *mut *mut gadcu_array) -> gadcu_status;
+    pub fn gadcu_array_random(ctx: *mut gadcu_ctx, dt: c_int, dims: D, seed: u64, normal: c_int, a: f64, b: f64, out: *mut *mut gadcu_array) -> gadcu_status;
+    pub fn gadcu_array_upload(a: *mut gadcu_array, pinned_host: *const c_void, stream_or_null: *mut c_void) -> gadcu_status;
+    pub fn gadcu_array_upload_async(a: *mut gadcu_array, pinned_host: *const c_void) -> gadcu_status;
+    pub fn gadcu_array_dtype(a: *const gadcu_array) -> c_int;
+    pub fn gadcu_array_is_scalar(a: *const gadcu_array) -> c_int;
+    pub fn gadcu_array_device_ptr(a: *const gadcu_array) -> *mut c_void;
+    // Check
+    pub fn gadcu_check_select_argmax(v0: D, v1: D, r0_or_null: D, r1_or_null: D, out: *mut gadcu_dim4) -> gadcu_status;
+    pub fn gadcu_check_flat(v: D, out: *mut gadcu_dim4) -> gadcu_status;
+    // algebras
+    pub fn gadcu_algebra_get_kind(alg: *const gadcu_algebra) -> c_int;
+    pub fn gadcu_algebra_num_nodes(alg: *const gadcu_algebra) -> usize;
+    // derived CompareAlgebra / ArrayAlgebra / MatrixAlgebra methods (compare.rs:24-66, array.rs:42-44, matrix.rs:28-31)
+    pub fn gadcu_min(g: A, a: V, b: V, out: O) -> gadcu_status;
+    pub fn gadcu_max(g: A, a: V, b: V, out: O) -> gadcu_status;
+    pub fn gadcu_abs(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_sign(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_relu(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_norm2(g: A, v: V, out: O) -> gadcu_status;
+    pub fn gadcu_matmul_nn(g: A, a: V, b: V, out: O) -> gadcu_status;
+    // user-defined nodes (graph.rs:106-165, store.rs:44-55)
+    pub fn gadcu_make_node(g: A, data: *mut gadcu_array, inputs: *const V, n: usize, vjp: gadcu_vjp_fn, user: *mut c_void,
+                           drop_user: Option<unsafe extern "C" fn(*mut c_void)>, out: O) -> gadcu_status;
+    pub fn gadcu_store_add_gradient(store: *mut gadcu_store, grad_algebra: A, arena: u32, index: u32, value: V) -> gadcu_status;
+    pub fn gadcu_store_ids(s: *const gadcu_store, out_indices: *mut u32, cap: usize) -> usize;
+    // CUDA-graph capture of everything issued between begin and end
+    pub fn gadcu_capture_begin(ctx: *mut gadcu_ctx) -> gadcu_status;
+    pub fn gadcu_capture_end(ctx: *mut gadcu_ctx, out: *mut *mut gadcu_capture) -> gadcu_status;
+    pub fn gadcu_capture_launch(c: *mut gadcu_capture) -> gadcu_status;
+    pub fn gadcu_capture_destroy(c: *mut gadcu_capture) -> gadcu_status;
+    // batched scalar tapes: one Graph1 tape per lane
+    pub fn gadcu_batched_create(ctx: *mut gadcu_ctx, dt: c_int, lanes: u64, out: *mut A) -> gadcu_status;
+    pub fn gadcu_batched_force(g: A, v: V, out: *mut *mut gadcu_array) -> gadcu_status;
+    pub fn gadcu_batched_rerun(s: *mut gadcu_store, columns: *const *mut gadcu_array, n: usize, gradients_out: *mut *mut gadcu_array) -> gadcu_status;
+    pub fn gadcu_batched_program_stats(s: *const gadcu_store, instructions: *mut u64, slots: *mut u64) -> gadcu_status;
+    // data parallelism
+    pub fn gadcu_comm_allreduce_sum_async(comm: *mut gadcu_comm, arrays: *const *mut gadcu_array, n: usize) -> gadcu_status;
+    pub fn gadcu_comm_join(comm: *mut gadcu_comm) -> gadcu_status;
+    pub fn gadcu_evaluate_gradients_dp(g: A, arena: u32, index: u32, seed: *mut gadcu_array, once: c_int, comm: *mut gadcu_comm,
+                                       out: *mut *mut gadcu_store) -> gadcu_status;
+    pub fn gadcu_evaluate_gradients_dp_with(g: A, arena: u32, index: u32, seed: *mut gadcu_array, once: c_int, comm: *mut gadcu_comm,
+                                            also: *const *mut gadcu_array, n_also: usize, out: *mut *mut gadcu_store) -> gadcu_status;
 }

@@ -104,6 +104,52 @@ def test_library_exports_every_declared_symbol():
     assert not leaked
 
 
+def _split_params(params: str):
+    """Top-level comma split of a C or Rust parameter list (function-pointer parameters contain commas of their own)."""
+    out, depth, cur = [], 0, ""
+    for ch in params:
+        if ch in "(<[":
+            depth += 1
+        elif ch in ")>]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip() and cur.strip() != "void":
+        out.append(cur.strip())
+    return out
+
+
+def test_rust_binding_declares_the_whole_header_with_matching_arity():
+    """rust/src/ffi.rs is what a gad maintainer would compile against libgadcu; there is no Rust
+    toolchain here, so at least keep it in step with include/gadcu.h: same entry points, same number of parameters,
+    same status codes."""
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "gadcu.h")).read(), flags=re.S)
+    rust = re.sub(r"//[^\n]*", "", open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read())
+    c_fns = {}
+    for m in re.finditer(r"GADCU_API\s+[\w\s\*]+?\b(gadcu_\w+)\s*\(", header):
+        start, depth, i = m.end(), 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(header[i], 0)
+            i += 1
+        c_fns[m.group(1)] = _split_params(header[start:i - 1])
+    r_fns = {}
+    for m in re.finditer(r"pub fn (gadcu_\w+)\s*\(", rust):
+        start, depth, i = m.end(), 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(rust[i], 0)
+            i += 1
+        r_fns[m.group(1)] = _split_params(rust[start:i - 1])
+    assert sorted(c_fns) == sorted(r_fns), sorted(set(c_fns) ^ set(r_fns))
+    wrong = {n: (len(c_fns[n]), len(r_fns[n])) for n in c_fns if len(c_fns[n]) != len(r_fns[n])}
+    assert not wrong, wrong
+    c_codes = dict(re.findall(r"(GADCU_ERR_\w+)\s*=\s*(\d+)", header))
+    r_codes = dict(re.findall(r"pub const (GADCU_ERR_\w+): gadcu_status = (\d+);", rust))
+    assert c_codes == r_codes
+
+
 def test_no_compute_without_gpu_is_an_error_not_a_fallback():
     """On a host without a GPU, creating a context fails with a CUDA error (status 8): the product
     never silently computes on the CPU."""
