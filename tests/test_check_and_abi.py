@@ -190,3 +190,32 @@ def test_header_is_plain_c_and_the_c_demo_links():
                               "-L", os.path.dirname(_lib.LIB_PATH), "-lgadcu", "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH),
                               "-o", os.path.join(tmp, "demo")], capture_output=True, text=True)
         assert res.returncode == 0, res.stderr
+
+
+def _build_cpp_reference_tests(out_path):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", os.path.join(root, "examples", "reference_tests.cc"),
+                           "-I", os.path.join(root, "include"), "-L", os.path.dirname(_lib.LIB_PATH), "-lgadcu",
+                           "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH), "-o", out_path], capture_output=True, text=True)
+
+
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_a_gpu():
+    """include/gadcu.hpp (the compiled-language mirror of gad's traits above the C ABI) builds warning-free, and the
+    reference tests written against it (examples/reference_tests.cc) link against libgadcu.so. Without a GPU the
+    program reports Error{Cuda} and exits non-zero: no CPU fallback."""
+    import shutil
+    import tempfile
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "reference_tests")
+        res = _build_cpp_reference_tests(exe)
+        assert res.returncode == 0, res.stderr
+        try:
+            import torch
+            has_gpu = torch.cuda.is_available()
+        except Exception:
+            has_gpu = False
+        if not has_gpu:
+            run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+            assert run.returncode == 2 and "gadcu::Error kind 8" in run.stdout, run.stdout
