@@ -55,6 +55,7 @@ _DIMS = ["moddims", "tile_as", "sum_as", "constant_as", "max_as", "argmax_as", "
 SIGNATURES = {
     "gadcu_last_error": (C.c_char_p, []),
     "gadcu_version": (C.c_char_p, []),
+    "gadcu_debug_gemm_schedule": (C.c_size_t, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gadcu_ctx_create": (C.c_int, [C.c_int, PP]),
     "gadcu_ctx_destroy": (C.c_int, [P]),
     "gadcu_ctx_synchronize": (C.c_int, [P]),

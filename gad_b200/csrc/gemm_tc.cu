@@ -356,11 +356,11 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
 // per band, so the band goes along the dimension whose own operand is the SMALLER one to keep resident.
 struct TileSched {
   uint32_t num_mt, num_nt, total, band, along_n;
-  __device__ __forceinline__ void decode(uint32_t t, uint32_t& mt, uint32_t& nt) const {
+  __host__ __device__ __forceinline__ void decode(uint32_t t, uint32_t& mt, uint32_t& nt) const {
     const uint32_t banded = along_n ? num_nt : num_mt, other = along_n ? num_mt : num_nt;
     const uint32_t band_size = band * other;
     const uint32_t b = t / band_size, r = t - b * band_size;
-    const uint32_t rows = min(band, banded - b * band);
+    const uint32_t rows = band < banded - b * band ? band : banded - b * band;
     const uint32_t o = r / rows, i = b * band + (r - o * rows);
     mt = along_n ? o : i;
     nt = along_n ? i : o;
@@ -386,7 +386,7 @@ struct StreamK {
 struct WorkIter {
   uint32_t u, dp_units, stride, total, unit_kb;
   uint32_t next_tile, end_tile, tile_step, kb0, kb1, part;
-  __device__ __forceinline__ WorkIter(uint32_t cluster, uint32_t clusters, uint32_t total_tiles, uint32_t splits, uint32_t kb_per_tile,
+  __host__ __device__ __forceinline__ WorkIter(uint32_t cluster, uint32_t clusters, uint32_t total_tiles, uint32_t splits, uint32_t kb_per_tile,
                                       const StreamK& sk)
       : u(cluster), dp_units((total_tiles - sk.rem) * splits), stride(clusters), total(total_tiles - sk.rem),
         unit_kb(kb_per_tile / splits), end_tile(total_tiles) {
@@ -400,7 +400,7 @@ struct WorkIter {
       kb0 = kb_per_tile - sk.tail_kb, kb1 = kb_per_tile, part = 1;
     }
   }
-  __device__ __forceinline__ bool next(Work& w) {
+  __host__ __device__ __forceinline__ bool next(Work& w) {
     if (u < dp_units) {
       const uint32_t half = u / total;
       w = Work{u - half * total, half, half * unit_kb, (half + 1) * unit_kb, 0u};
@@ -796,15 +796,66 @@ bool gemm_tc_supported(const GemmArgs& g) {
 namespace {
 
 // split the k range in two when that fills the last wave markedly better (see the kernel)
-uint32_t choose_splits(gadcu_ctx* ctx, const GemmArgs& g, int bk) {
+uint32_t choose_splits_for(int sm_count, uint64_t M, uint64_t N, uint64_t K, bool accumulate, int bk) {
   static const int split_mode = [] { const char* e = getenv("GADCU_GEMM_SPLITK"); return e ? atoi(e) : -1; }();  // -1 auto, 1 off, 2 force
-  const uint64_t tiles = (g.M / 256) * (g.N / 256), kb = g.K / uint64_t(bk);
-  if (g.M % 256 || g.N % 256 || g.K % uint64_t(bk)) return 1;
-  if (g.accumulate || kb % 2 != 0 || kb / 2 < 8 || split_mode == 1) return 1;
+  const uint64_t tiles = (M / 256) * (N / 256), kb = K / uint64_t(bk);
+  if (M % 256 || N % 256 || K % uint64_t(bk)) return 1;
+  if (accumulate || kb % 2 != 0 || kb / 2 < 8 || split_mode == 1) return 1;
   if (split_mode == 2) return 2;
-  const uint64_t c = uint64_t(ctx->sm_count / 2);
+  const uint64_t c = uint64_t(sm_count / 2);
   auto wave_eff = [&](uint64_t units) { return double(units) / double((units + c - 1) / c * c); };
   return wave_eff(2 * tiles) > wave_eff(tiles) + 0.05 ? 2 : 1;
+}
+uint32_t choose_splits(gadcu_ctx* ctx, const GemmArgs& g, int bk) { return choose_splits_for(ctx->sm_count, g.M, g.N, g.K, g.accumulate, bk); }
+
+// Everything the pair kernel's work distribution depends on, decided on the host from the shape alone (so it can be
+// enumerated and checked without a GPU: gadcu_debug_gemm_schedule, tests/test_gemm_schedule.py).
+struct PairPlan {
+  uint64_t clusters;            // 2-CTA clusters launched
+  uint32_t splits;              // 1, or 2: every tile as two k halves (tile-pushing mode; stream-K switched off)
+  uint32_t rem, tail_kb;        // last-wave split (WorkIter): tiles in the ragged last wave, k-blocks of their tails; 0 = none
+  uint32_t band_arg;            // band | along_n << 16 | l2 hints << 17 (TileSched)
+  uint32_t num_kb;              // k-blocks per tile
+};
+PairPlan plan_pair(int sm_count, bool comm_inflight, uint64_t M, uint64_t N, uint64_t K, int bkt, bool accumulate,
+                   int push_splits /* 0: not the tile-pushing mode */, bool have_flags) {
+  PairPlan p{};
+  const uint64_t tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  // while an overlapped all-reduce is in flight a few SM pairs are left to its CTAs (a persistent CTA per SM would
+  // otherwise keep them out until the GEMM ends)
+  static const uint64_t reserve = [] { const char* e = getenv("GADCU_DP_RESERVE_CLUSTERS"); return e ? uint64_t(atoi(e)) : uint64_t(0); }();
+  const uint64_t usable = uint64_t(sm_count / 2) - (comm_inflight ? reserve : 0);
+  // the ragged last wave is shared out stream-K fashion (see WorkIter; GADCU_GEMM_STREAMK=0 for the older split-in-two)
+  static const bool streamk_on = [] { const char* e = getenv("GADCU_GEMM_STREAMK"); return !e || atoi(e) != 0; }();
+  static const uint64_t min_tail = [] { const char* e = getenv("GADCU_GEMM_SK_MIN_TAIL"); return e ? uint64_t(atoi(e)) : uint64_t(8); }();
+  const bool streamk = streamk_on && !push_splits && have_flags;
+  const uint64_t kb_per_tile = (K + uint64_t(bkt) - 1) / uint64_t(bkt);
+  p.num_kb = uint32_t(kb_per_tile);
+  p.clusters = std::min<uint64_t>(tiles * 2, usable);  // (a cluster without work exits at once)
+  if (streamk && tiles % p.clusters != 0) {
+    const uint64_t rem = tiles % p.clusters, helpers = p.clusters - rem, per_helper = (rem + helpers - 1) / helpers;
+    const uint64_t tail = kb_per_tile / (per_helper + 1);  // head (KB - tail) = per_helper tails
+    // worth it when it shortens the launch by 3 % or more: 512 tiles (6.92 waves: 1 % to gain) measured 5 % SLOWER split
+    // than whole — twelve 9-block tails per helper are epilogue-bound and the heads' read-add-store epilogue is exposed
+    const double gain = double(tail) / double((tiles / p.clusters + 1) * kb_per_tile);
+    // ... and not for a single partial wave that already covers most of the chip (64 tiles on 74 clusters, the 1024-row
+    // shards of an 8-GPU step): no gain alone (0.132 ms either way: the idle SMs' power goes to the busy ones) and 2.5 %
+    // slower inside the 8-GPU step (516 vs 503 steps/s), where the idle SMs are what the exchange kernels run on
+    const bool lone_wide_wave = tiles < p.clusters && tiles * 2 > p.clusters;
+    if (tail >= min_tail && gain >= 0.03 && !lone_wide_wave) p.rem = uint32_t(rem), p.tail_kb = uint32_t(tail);
+  }
+  p.splits = push_splits ? uint32_t(push_splits) : (streamk ? 1u : choose_splits_for(sm_count, M, N, K, accumulate, bkt));  // (push: the exchange laid its staging out for this)
+  // band of tiles whose operand slices (hi + lo, 8 bytes per element) should fit in about half of L2 (126 MB), along
+  // the dimension with the smaller operand: that operand is then read from HBM once, the other once per band
+  static const uint32_t band_override = [] { const char* e = getenv("GADCU_GEMM_BAND"); return e ? uint32_t(atoi(e)) : 0u; }();
+  const uint64_t slice_bytes = 256ull * (K / p.splits) * 8;  // one tile-row of A or tile-column of B (of one k half)
+  uint32_t band = uint32_t(std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(slice_bytes, 1)));
+  const uint32_t along_n = N < M ? 1u : 0u;   // fewer tile-columns than tile-rows: B is the smaller operand
+  band = std::min<uint32_t>(band, uint32_t(((along_n ? N : M) + 255) / 256));
+  if (band_override) band = band_override & 0xffffu;
+  static const uint32_t l2_hints = [] { const char* e = getenv("GADCU_GEMM_L2_HINTS"); return e ? uint32_t(atoi(e)) & 3u : 0u; }();
+  p.band_arg = band | (((band_override ? (band_override >> 16) : along_n) & 1u) << 16) | (l2_hints << 17);
+  return p;
 }
 
 template <int BKT, int S>
@@ -819,30 +870,10 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   const uint64_t a_mn_ext = a_mn ? lda : g.M, a_k_ext = a_mn ? g.K : lda, b_mn_ext = b_mn ? ldb : g.N, b_k_ext = b_mn ? g.K : ldb;
   CUtensorMap mah = make_map(ah, a_mn, a_mn_ext, a_k_ext, lda, 128, BKT, k_swz), mal = make_map(al, a_mn, a_mn_ext, a_k_ext, lda, 128, BKT, k_swz);
   CUtensorMap mbh = make_map(bh, b_mn, b_mn_ext, b_k_ext, ldb, 128, BKT, k_swz), mbl = make_map(bl, b_mn, b_mn_ext, b_k_ext, ldb, 128, BKT, k_swz);
-  const uint64_t tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256);
-  // while an overlapped all-reduce is in flight a few SM pairs are left to its CTAs (a persistent CTA per SM would
-  // otherwise keep them out until the GEMM ends)
-  static const uint64_t reserve = [] { const char* e = getenv("GADCU_DP_RESERVE_CLUSTERS"); return e ? uint64_t(atoi(e)) : uint64_t(0); }();
-  const uint64_t usable = uint64_t(ctx->sm_count / 2) - (ctx->comm_inflight.load(std::memory_order_relaxed) ? reserve : 0);
-  // the ragged last wave is shared out stream-K fashion (see WorkIter; GADCU_GEMM_STREAMK=0 for the older split-in-two)
-  static const bool streamk_on = [] { const char* e = getenv("GADCU_GEMM_STREAMK"); return !e || atoi(e) != 0; }();
-  static const uint64_t min_tail = [] { const char* e = getenv("GADCU_GEMM_SK_MIN_TAIL"); return e ? uint64_t(atoi(e)) : uint64_t(8); }();
-  const bool streamk = streamk_on && !g.push && ctx->gemm_flags != nullptr;
-  const uint64_t kb_per_tile = (g.K + BKT - 1) / BKT;
-  const uint64_t clusters = std::min<uint64_t>(tiles * 2, usable);  // (a cluster without work exits at once)
-  StreamK sk{0u, 0u, ctx->gemm_flags, nullptr};
-  if (streamk && tiles % clusters != 0) {
-    const uint64_t rem = tiles % clusters, helpers = clusters - rem, per_helper = (rem + helpers - 1) / helpers;
-    const uint64_t tail = kb_per_tile / (per_helper + 1);  // head (KB - tail) = per_helper tails
-    // worth it when it shortens the launch by 3 % or more: 512 tiles (6.92 waves: 1 % to gain) measured 5 % SLOWER split
-    // than whole — twelve 9-block tails per helper are epilogue-bound and the heads' read-add-store epilogue is exposed
-    const double gain = double(tail) / double((tiles / clusters + 1) * kb_per_tile);
-    // ... and not for a single partial wave that already covers most of the chip (64 tiles on 74 clusters, the 1024-row
-    // shards of an 8-GPU step): no gain alone (0.132 ms either way: the idle SMs' power goes to the busy ones) and 2.5 %
-    // slower inside the 8-GPU step (516 vs 503 steps/s), where the idle SMs are what the exchange kernels run on
-    const bool lone_wide_wave = tiles < clusters && tiles * 2 > clusters;
-    if (tail >= min_tail && gain >= 0.03 && !lone_wide_wave) sk.rem = uint32_t(rem), sk.tail_kb = uint32_t(tail);
-  }
+  const PairPlan plan = plan_pair(ctx->sm_count, ctx->comm_inflight.load(std::memory_order_relaxed), g.M, g.N, g.K, BKT, g.accumulate,
+                                  g.push ? int(g.push->splits) : 0, ctx->gemm_flags != nullptr);
+  const uint64_t clusters = plan.clusters;
+  StreamK sk{plan.rem, plan.tail_kb, ctx->gemm_flags, nullptr};
   static const int trace_at = [] { const char* e = getenv("GADCU_SK_TRACE"); return e ? atoi(e) : 0; }();  // trace the n-th launch
   static int trace_count = 0;
   const bool trace_on = trace_at && ++trace_count == trace_at;
@@ -850,18 +881,7 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
     GADCU_CUDA(cudaMallocManaged(&sk.trace, 74 * 16 * 4 * 8));
     memset(sk.trace, 0, 74 * 16 * 4 * 8);
   }
-  // band of tiles whose operand slices (hi + lo, 8 bytes per element) should fit in about half of L2 (126 MB), along
-  // the dimension with the smaller operand: that operand is then read from HBM once, the other once per band
-  static const uint32_t band_override = [] { const char* e = getenv("GADCU_GEMM_BAND"); return e ? uint32_t(atoi(e)) : 0u; }();
-  uint32_t splits = streamk ? 1u : choose_splits(ctx, g, BKT);
-  if (g.push) splits = g.push->splits;  // (the exchange laid its staging out for this)
-  const uint64_t slice_bytes = 256ull * (g.K / splits) * 8;  // one tile-row of A or tile-column of B (of one k half)
-  uint32_t band = uint32_t(std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(slice_bytes, 1)));
-  const uint32_t along_n = g.N < g.M ? 1u : 0u;   // fewer tile-columns than tile-rows: B is the smaller operand
-  band = std::min<uint32_t>(band, uint32_t(((along_n ? g.N : g.M) + 255) / 256));
-  if (band_override) band = band_override & 0xffffu;
-  static const uint32_t l2_hints = [] { const char* e = getenv("GADCU_GEMM_L2_HINTS"); return e ? uint32_t(atoi(e)) & 3u : 0u; }();
-  const uint32_t band_arg = band | (((band_override ? (band_override >> 16) : along_n) & 1u) << 16) | (l2_hints << 17);
+  const uint32_t splits = plan.splits, band_arg = plan.band_arg;
   if (splits == 2 && !g.push) GADCU_CUDA(cudaMemsetAsync(g.C, 0, size_t(g.M) * g.N * 4, ctx->stream));
   static std::once_flag once;
   std::call_once(once, [] {
@@ -911,6 +931,37 @@ static const float* split_operand(gadcu_ctx* ctx, const float* x, uint64_t R, ui
     owner->split_rows = R;
   }
   return hi;
+}
+
+// The work list of every cluster for an f32 product of this shape, computed on the host with the kernel's own iterator
+// (no device needed). Rows of 6: cluster, tile row, tile column, first k-block, end k-block, part (0 whole unit, 1 tail,
+// 2 head). info[8] = clusters, splits, rem, tail_kb, k-blocks per tile, band, along_n, tile count. Returns the number of
+// rows the schedule has (which may exceed `cap`; only `cap` are written).
+size_t gemm_schedule_debug(int sm_count, uint64_t M, uint64_t N, uint64_t K, int push_splits, uint32_t* rows, size_t cap, uint32_t* info) {
+  const int bkt = pair_variant() == 1 || pair_variant() == 0 ? 32 : 16;
+  const PairPlan plan = plan_pair(sm_count, false, M, N, K, bkt, false, push_splits, true);
+  const uint32_t num_mt = uint32_t((M + 255) / 256), num_nt = uint32_t((N + 255) / 256);
+  const TileSched sched{num_mt, num_nt, num_mt * num_nt, plan.band_arg & 0xffffu, (plan.band_arg >> 16) & 1u};
+  if (info) {
+    const uint32_t v[8] = {uint32_t(plan.clusters), plan.splits, plan.rem, plan.tail_kb, plan.num_kb, sched.band, sched.along_n, sched.total};
+    for (int i = 0; i < 8; i++) info[i] = v[i];
+  }
+  const StreamK sk{plan.rem, plan.tail_kb, nullptr, nullptr};
+  size_t n = 0;
+  for (uint32_t c = 0; c < plan.clusters; c++) {
+    WorkIter work(c, uint32_t(plan.clusters), sched.total, plan.splits, plan.num_kb, sk);
+    Work w;
+    while (work.next(w)) {
+      if (n < cap) {
+        uint32_t mt, nt;
+        sched.decode(w.tile, mt, nt);
+        const uint32_t row[6] = {c, mt, nt, w.kb0, w.kb1, w.part};
+        for (int i = 0; i < 6; i++) rows[n * 6 + i] = row[i];
+      }
+      n++;
+    }
+  }
+  return n;
 }
 
 uint32_t gemm_push_splits(gadcu_ctx* ctx, const GemmArgs& g) { return choose_splits(ctx, g, pair_variant() == 1 ? 32 : 16); }

@@ -98,6 +98,7 @@ struct GemmArgs {
 void launch_gemm(gadcu_ctx* ctx, const GemmArgs& g);
 bool gemm_tc_supported(const GemmArgs& g);  // tcgen05 3xTF32 path applies
 bool gemm_push_supported(const GemmArgs& g);  // ... and its CTA-pair kernel, which can push tiles to peers
+size_t gemm_schedule_debug(int sm_count, uint64_t M, uint64_t N, uint64_t K, int push_splits, uint32_t* rows, size_t cap, uint32_t* info);  // gemm_tc.cu
 uint32_t gemm_push_splits(gadcu_ctx* ctx, const GemmArgs& g);  // 1 or 2: how the pair kernel would split k for this shape
 
 }  // namespace k

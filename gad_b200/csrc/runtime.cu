@@ -135,6 +135,9 @@ extern "C" {
 
 const char* gadcu_last_error(void) { return gadcu::last_error().c_str(); }
 const char* gadcu_version(void) { return "gadcu 0.1 (sm_100a)"; }
+size_t gadcu_debug_gemm_schedule(int sm_count, uint64_t M, uint64_t N, uint64_t K, int push_splits, uint32_t* rows6, size_t cap, uint32_t* info8) {
+  return gadcu::k::gemm_schedule_debug(sm_count, M, N, K, push_splits, rows6, cap, info8);
+}
 
 gadcu_status gadcu_ctx_create(int device, gadcu_ctx** out) {
   return guard([&] {

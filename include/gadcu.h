@@ -78,6 +78,14 @@ typedef struct {
 
 GADCU_API const char* gadcu_last_error(void);
 GADCU_API const char* gadcu_version(void);
+/* Host-only introspection (no device needed): the work list the tensor-core GEMM would give every 2-CTA cluster for an
+ * f32 product [M,K]x[K,N] on a GPU with `sm_count` SMs, from the kernel's own scheduling code. rows6: one row per work
+ * item = {cluster, tile row, tile column, first k-block, end k-block, part (0 whole unit, 1 tail, 2 head of a split
+ * tile)}; info8 = {clusters, k splits, last-wave tiles, tail k-blocks, k-blocks per tile, band, band along N, tiles}.
+ * push_splits: 0, or the k splits of the tile-pushing data-parallel mode. Returns the number of work items (may exceed
+ * cap). Used by tests/test_gemm_schedule.py to check coverage and pairing for many shapes without a GPU. */
+GADCU_API size_t gadcu_debug_gemm_schedule(int sm_count, uint64_t M, uint64_t N, uint64_t K, int push_splits, uint32_t* rows6,
+                                           size_t cap, uint32_t* info8);
 
 /* ---- context: device, stream, caching allocator, error slot -------------------------------- */
 GADCU_API gadcu_status gadcu_ctx_create(int device, gadcu_ctx** out);

@@ -145,6 +145,7 @@ extern "C" {
 // counterpart in the reference (tests/test_check_and_abi.py keeps this file and the header in step)
 extern "C" {
     pub fn gadcu_version() -> *const c_char;
+    pub fn gadcu_debug_gemm_schedule(sm_count: c_int, m: u64, n: u64, k: u64, push_splits: c_int, rows6: *mut u32, cap: usize, info8: *mut u32) -> usize;
     pub fn gadcu_ctx_stream(ctx: *mut gadcu_ctx) -> *mut c_void;
     pub fn gadcu_ctx_set_fusion(ctx: *mut gadcu_ctx, fuse: c_int) -> gadcu_status;
     pub fn gadcu_ctx_set_lazy(ctx: *mut gadcu_ctx, enable: c_int, min_elements: u64) -> gadcu_status;
