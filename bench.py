@@ -420,7 +420,7 @@ def secondary_metrics(ctx, ext, torch, gb, wl, pk, args):
         "metric": "grad-sweep HBM GB/s", "workload": "C3 64Mi-element exp/log/mul/add + sum, f32, reverse sweep", "value": gbs, "unit": "GB/s",
         "ms_per_sweep": ms_sweep, "launches_per_sweep": int(sweep_launches),
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                     "frac_of_8TBs": gbs / 8000.0, "traffic": None, "algorithmic_bytes": alg_bytes,
+                     "frac_of_8TBs": gbs / 8000.0, "traffic": ncu_traffic("lane_program_c3_sweep"), "algorithmic_bytes": alg_bytes,
                      "note": "algorithmic = 4 passes (read x,y; write gx,gy); the per-node sweep materialises more (see DESIGN.md)"},
         "fwd_plus_sweep_ms": ms_fb, "fwd_plus_sweep_gbs": 6 * n * 4 / (ms_fb * 1e-3) / 1e9}
     del keep, g, vx, vy, z, x, y
@@ -463,7 +463,8 @@ def secondary_metrics(ctx, ext, torch, gb, wl, pk, args):
         "rerun_ms_wall": rerun_wall * 1e3, "rerun_grads_per_s_wall": lanes / rerun_wall,
         "program_instructions": stats["instructions"], "program_slots": stats["slots"],
         "roofline": {"bound": "hbm", "achieved": gps * alg / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": gps * alg / 1e9 / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_gradient": alg}}
+                     "frac": gps * alg / 1e9 / pk["hbm_gbs"], "traffic": ncu_traffic("lane_program_c2"),
+                     "algorithmic_bytes_per_gradient": alg, "algorithmic_bytes": alg * lanes}}
     del cols, res
 
     out["hvp"] = hvp_metric(ctx, ext, torch, wl, None, 1, 0)
