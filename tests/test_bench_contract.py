@@ -65,3 +65,35 @@ def test_our_arm_refuses_to_run_without_a_gpu():
                          timeout=600, cwd=ROOT)
     assert res.returncode != 0
     assert not _json_lines(res.stdout), "a bench line without a GPU would be a CPU fallback"
+
+
+def test_committed_bench_lines_carry_the_whole_contract():
+    """profiles/r01_bench_*.json are the lines the B200 runs printed: every key the contract names is there, with the
+    roofline / cpu_baseline / e2e / clocks objects filled and no model keys in `config`."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_final.json")) + glob.glob(os.path.join(ROOT, "profiles", "r01_bench_n[248].json")))
+    assert len(files) == 4
+    for path in files:
+        line = _json_lines(open(path).read())[-1]
+        for k in ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                  "config", "clocks", "e2e", "gpu_launches", "roofline"]:
+            assert k in line, (path, k)
+        assert line["metric"] == "MLP fwd+bwd steps/s" and line["unit"] == "steps/s" and line["scaling"] == "strong" and line["dtype"] == "f32"
+        assert line["vs_baseline"] is None and line["data"] == "synthetic" and line["warmup"] >= 3 and line["gpu_launches"] > 0
+        assert "workload" in line["config"] and "model" not in line["config"] and "l2" in line["config"]
+        n = line["n_gpus"]
+        assert os.path.basename(path) == ("r01_bench_final.json" if n == 1 else f"r01_bench_n{n}.json")
+        r = line["roofline"]
+        assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+        e = line["e2e"]
+        assert e["unit"] == "steps/s" and 0 < e["value"] <= line["value"] * 1.02 and e["h2d_bytes_per_step"] == 8192 * 4096 * 4 * 2 and e["d2h_bytes_per_step"] == 4 * n
+        c = line["clocks"]
+        assert c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"] and not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
+        if n == 1:
+            cb = line["cpu_baseline"]
+            assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb
+            sec = line["secondary"]
+            for key in ["grad_sweep", "batched_tape", "hvp", "graph_replay", "scalar_tape"]:
+                assert key in sec, key
+            assert sec["grad_sweep"]["roofline"]["bound"] == "hbm" and sec["batched_tape"]["roofline"]["bound"] == "hbm"
+            assert sec["grad_sweep"]["cpu_baseline"]["kind"] == "port" and sec["batched_tape"]["cpu_baseline"]["cores"] >= 1
