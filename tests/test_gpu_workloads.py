@@ -366,3 +366,34 @@ def test_captured_mlp_step_replays_bit_identically(ctx):
     fresh = wl.mlp_step(ctx, ctx.array(X2), dW, db, dT)
     assert out[0].item() == fresh[0].item()
     assert np.array_equal(out[1][2].numpy(), fresh[1][2].numpy())
+
+
+def test_device_results_against_the_committed_oracle_fixtures(ctx):
+    """tests/golden/oracle_array_fixtures.npz: the oracle's outputs for C3 (n = 257), C4 (B = 8, D = 4) and batched
+    Rosenbrock (8 variables, 5 lanes) on seeded inputs, committed with the script that made them. Same bounds as the
+    live-oracle tests above: batched f64 tapes bit for bit, f32 elementwise VJPs within a few ulp of the summands,
+    GEMM-backed gradients within f32 rounding."""
+    import os
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_array_fixtures.npz"))
+    # C3
+    x, y = fx["c3_x"], fx["c3_y"]
+    z, gx, gy = wl.c3_step(ctx, ctx.array(x), ctx.array(y))
+    eps = np.finfo(np.float32).eps
+    prod = np.abs(np.exp(x.astype(np.float64)) * np.log(y.astype(np.float64)))
+    assert np.all(np.abs(to_np(gx).reshape(-1).astype(np.float64) - fx["c3_gx"].astype(np.float64)) <= 12 * eps * (prod + 1.0))
+    assert ulp_diff(to_np(gy).reshape(-1), fx["c3_gy"]) <= 4
+    assert abs(z.item() - float(fx["c3_z"])) <= 64 * x.size * eps
+    # C4
+    X, Ws, bs, T = fx["mlp_X"], list(fx["mlp_W"]), list(fx["mlp_b"]), fx["mlp_T"]
+    loss, gW, gb_ = wl.mlp_step(ctx, ctx.array(X), [ctx.array(w) for w in Ws], [ctx.array(b) for b in bs], ctx.array(T))
+    assert abs(loss.item() - float(fx["mlp_loss"])) <= 1e-4 * abs(float(fx["mlp_loss"]))
+    for l in range(3):
+        a, o = to_np(gW[l])[:, :, 0, 0].astype(np.float64), fx["mlp_gW"][l].astype(np.float64)
+        assert np.max(np.abs(a - o)) <= 4e-5 * np.max(np.abs(o)) * np.sqrt(X.shape[0]), l
+        a, o = to_np(gb_[l])[:, :, 0, 0].astype(np.float64).reshape(-1), fx["mlp_gb"][l].astype(np.float64).reshape(-1)
+        assert np.max(np.abs(a - o)) <= 4e-5 * np.max(np.abs(o)) * np.sqrt(X.shape[0]), l
+    # C2 / C1
+    rx = fx["ros_x"]
+    _, _, grads, _ = wl.rosenbrock_batched_gradients(ctx, [ctx.array(rx[i]) for i in range(rx.shape[0])])
+    got = np.stack([to_np(c)[:, 0, 0, 0] for c in grads])
+    assert np.array_equal(got, fx["ros_g"])

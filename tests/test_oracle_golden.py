@@ -112,3 +112,45 @@ def test_structure_pins(oracle):
     store = g.evaluate_gradients_once(e.gid(), np.float32(1.0))
     assert store.get(a1.gid(), like=a1) is None and store.get(b.gid(), like=b) is None
     assert store.get(c.gid(), like=c).data() == 0.0 and store.get(d.gid(), like=d).data() == 1.0
+
+
+def test_oracle_reproduces_its_array_fixtures(oracle):
+    """tests/golden/oracle_array_fixtures.npz (made by tests/golden/make_array_fixtures.py): the oracle's outputs for the
+    array workloads at toy sizes. Recomputed bit for bit (no drift of the checker), and the stored values themselves are
+    checked against f64 closed forms."""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    fx = np.load(os.path.join(here, "oracle_array_fixtures.npz"))
+    spec = importlib.util.spec_from_file_location("make_array_fixtures", os.path.join(here, "make_array_fixtures.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    inp = mod.inputs()
+    for k, v in inp.items():
+        assert np.array_equal(fx[k], v), k  # the seeded inputs are what the file says
+    out = mod.outputs(inp)
+    for k, v in out.items():
+        assert np.array_equal(fx[k], v), k
+    # closed forms in f64
+    x, y = fx["c3_x"].astype(np.float64), fx["c3_y"].astype(np.float64)
+    eps = np.finfo(np.float32).eps
+    assert np.all(np.abs(fx["c3_gx"] - (np.exp(x) * np.log(y) + 1)) <= 6 * eps * (np.abs(np.exp(x) * np.log(y)) + 1))
+    assert np.allclose(fx["c3_gy"], np.exp(x) / y, rtol=8 * eps, atol=0)
+    assert abs(float(fx["c3_z"]) - float(np.sum(np.exp(x) * np.log(y) + x))) <= 64 * x.size * eps
+    X, W, b, T = (fx[k].astype(np.float64) for k in ["mlp_X", "mlp_W", "mlp_b", "mlp_T"])
+    h, hs = X, []
+    for l in range(3):
+        z = h @ W[l] + b[l]
+        hs.append(h)
+        h = np.tanh(z) if l < 2 else z
+    delta = T - h
+    assert abs(float(fx["mlp_loss"]) - float(np.sum(delta * delta))) <= 1e-5 * float(np.sum(delta * delta))
+    g = -2 * delta
+    for l in (2, 1, 0):
+        assert np.allclose(fx["mlp_gW"][l], hs[l].T @ g, rtol=1e-4, atol=1e-5), l
+        assert np.allclose(fx["mlp_gb"][l].reshape(-1), g.sum(axis=0), rtol=1e-4, atol=1e-5), l
+        if l:
+            g = (g @ W[l].T) * (1 - np.tanh(hs[l - 1] @ W[l - 1] + b[l - 1]) ** 2)
+    rx = fx["ros_x"]
+    import programs
+    assert np.allclose(fx["ros_g"], programs.rosenbrock_grad_closed_form(rx), rtol=1e-11, atol=1e-9)
