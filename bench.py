@@ -133,28 +133,41 @@ def host_cores() -> int:
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores (the ONLY use of oracle/ here)
 # ---------------------------------------------------------------------------------------------------
-def cpu_mlp_steps_per_s(rows: int, threads: int, repeats: int = 1):
+def oracle_module():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_py
-    rng = np.random.default_rng(5)
+    return oracle_py
+
+
+def cpu_gemm_kind(oracle_py, threads: int) -> str:
+    """The reference's arrays are ArrayFire's, whose CPU backend hands matmul to a BLAS sgemm; the port does the same when
+    the host has one (the OpenBLAS numpy bundles), else it falls back to its own blocked loop and says so."""
+    path = oracle_py.find_blas()
+    if path and oracle_py.set_blas(path, threads):
+        return "sgemm of " + os.path.basename(path).split("-")[0] + " (OpenBLAS bundled with numpy), as ArrayFire-CPU calls a BLAS"
+    return "the port's own column-blocked loop, NOT a BLAS (none found on this host): understates an ArrayFire-CPU build"
+
+
+def synthetic_mlp_host(rows: int, seed_shift: int = 0):
+    rng = np.random.default_rng(5 + seed_shift)
     X = rng.standard_normal((rows, D)).astype(np.float32)
     Ws = [(rng.standard_normal((D, D)) / np.sqrt(D)).astype(np.float32) for _ in range(L)]
     bs = [np.full((1, D), 0.01, np.float32) for _ in range(L)]
     T = rng.standard_normal((rows, D)).astype(np.float32)
-    best = None
-    for _ in range(repeats):
-        _, _, _, secs = oracle_py.mlp_step(X, Ws, bs, T, nthreads=threads)
-        best = secs if best is None else min(best, secs)
-    # a full step is B_TOTAL/rows of these (every GEMM, elementwise pass and reduction is linear in rows)
-    return 1.0 / (best * (B_TOTAL / rows)), best
+    return X, Ws, bs, T
+
+
+def cpu_mlp_step_seconds(oracle_py, rows: int, threads: int, data=None):
+    X, Ws, bs, T = data if data is not None else synthetic_mlp_host(rows)
+    loss, gW, gb_, secs = oracle_py.mlp_step(X, Ws, bs, T, nthreads=threads)
+    return secs, (loss, gW, gb_)
 
 
 def cpu_secondary(threads: int):
     """The restated CPU path beside the secondary metrics, each on a bounded sample (about a second of CPU work):
     C1 one scalar Rosenbrock-64 tape on one core, C2 the same tape looped over lanes on all cores, C3 the HostArray tape
     (one core: the reference's CPU arrays are single-threaded per op) with the reverse sweep timed on its own."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_py
+    oracle_py = oracle_module()
     rng = np.random.default_rng(2)
     out = {}
     x1 = -1.2 + 2.4 * rng.random((64, 1024))
@@ -176,25 +189,37 @@ def cpu_secondary(threads: int):
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU path for the same config and metric. The reference itself (Rust + the arrayfire
+    crate) cannot be built in this image, so this is oracle/ (kind "port") with all host cores. Every timed step is one
+    full C4 step over `rows` batch rows at full width; rows = the whole batch when the run then still ends within a few
+    minutes, otherwise the largest power-of-two share that does (steps/s scaled by 8192 / rows: work is linear in rows)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    oracle_py = oracle_module()
     threads = host_cores()
-    rows = 512  # ~4 s per step on 16 cores
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_mlp_steps_per_s(rows, threads)
-    vals, times = [], []
-    for _ in range(max(1, min(args.steps, 5))):
-        v, t = cpu_mlp_steps_per_s(rows, threads)
-        vals.append(v)
-        times.append(t)
-    v = float(np.mean(vals))
-    sample = f"{rows} of {B_TOTAL} batch rows at full width D={D}, L={L}; steps/s scaled by {B_TOTAL // rows}x (work is linear in rows)"
+    gemm = cpu_gemm_kind(oracle_py, threads)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    t_cal, _ = cpu_mlp_step_seconds(oracle_py, 1024, threads)  # calibration (untimed): one eighth of the batch
+    rows = B_TOTAL
+    budget = float(os.environ.get("GADCU_REF_BUDGET_S", "200"))
+    while rows > 1024 and (steps + warmup) * t_cal * (rows / 1024.0) > budget:
+        rows //= 2
+    data = synthetic_mlp_host(rows)
+    for _ in range(warmup):
+        cpu_mlp_step_seconds(oracle_py, rows, threads, data)
+    times = [cpu_mlp_step_seconds(oracle_py, rows, threads, data)[0] for _ in range(steps)]
+    scale = B_TOTAL // rows
+    sec_per_step = float(np.mean(times)) * scale
+    v = 1.0 / sec_per_step
+    sample = (f"{rows} of {B_TOTAL} batch rows at full width D={D}, L={L}" +
+              ("" if scale == 1 else f"; steps/s scaled by {scale}x (work is linear in rows)") + f"; matmul = {gemm}")
     line = {"impl": "reference", "metric": "MLP fwd+bwd steps/s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
-            "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong",
+            "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C4 3-layer tanh MLP {D}-wide, batch {B_TOTAL}, f32, Graph1 fwd + reverse sweep", "global_batch": B_TOTAL},
-            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": f"C4 3-layer tanh MLP {D}-wide, batch {B_TOTAL}, f32, Graph1 fwd + reverse sweep", "global_batch": B_TOTAL,
+                       "rows_timed_per_step": rows},
+            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample, "gemm": gemm},
             "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference (Rust crate gad + arrayfire) cannot be built in this image; this is oracle/, a C++ port of its CPU tape"}
     print(json.dumps(line), flush=True)
@@ -203,6 +228,25 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+def ncu_traffic_entry(kernel: str):
+    """(bytes per launch, "profiles/<capture>@<commit>") of `kernel` from the committed ncu --set full capture: the DRAM
+    bytes are a property of the kernel at that commit, measured once under the profiler, not of this run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            e = json.load(f).get(kernel)
+        if isinstance(e, dict):
+            return e.get("bytes"), f"profiles/{e.get('source')}@{e.get('commit')}"
+        return e, "profiles/ncu_traffic.json"
+    except Exception:
+        return None, None
+
+
+def rel_err(got, want) -> float:
+    """max |got - want| / max |want| in f64."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    return float(np.abs(got - want).max() / max(float(np.abs(want).max()), 1e-300))
+
+
 def run_ours(args):
     import torch
     import gad_b200 as gb
@@ -232,9 +276,13 @@ def run_ours(args):
 
     from gad_b200 import dp
     rows = dp.even_rows(B_TOTAL, world)
-    # synthetic data of the named shapes: X~N(0,1) seed 5, W_l~N(0,1/D) seeds 6-8, b=0.01, target~N(0,1) seed 9
-    X = ctx.random((rows, D), 5 + 100 * rank, normal=True, a=0.0, b=1.0)
-    T = ctx.random((rows, D), 9 + 100 * rank, normal=True, a=0.0, b=1.0)
+
+    # synthetic data of the named shapes: X~N(0,1) seed 5, W_l~N(0,1/D) seeds 6-8, b=0.01, target~N(0,1) seed 9;
+    # rank r holds rows [r rows, (r+1) rows) of the batch, generated from its own seeds
+    def shard(r):
+        return (ctx.random((rows, D), 5 + 100 * r, normal=True, a=0.0, b=1.0), ctx.random((rows, D), 9 + 100 * r, normal=True, a=0.0, b=1.0))
+
+    X, T = shard(rank)
     Ws = [ctx.random((D, D), 6 + l, normal=True, a=0.0, b=1.0 / np.sqrt(D)) for l in range(L)]
     bs = [ctx.array(np.full((1, D), 0.01, np.float32)) for _ in range(L)]
 
@@ -319,67 +367,217 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, e2e_steps)
     e2e = {"value": e2e_steps / (ms_e2e / 1000.0), "unit": "steps/s", "h2d_bytes_per_step": int(2 * rows * D * 4 * world),
            "d2h_bytes_per_step": int(4 * world), "ms_per_step": ms_e2e / e2e_steps}
+    del bufs
 
-    hvp_multi = None
-    if world > 1 and not args.headline_only:
-        hvp_multi = hvp_metric(ctx, ext, torch, wl, comm, world, rank, dist)
+    pk = peaks()
+    secondary = {}
+    dp_check = None
+    if world > 1:
+        try:  # untimed: the exchange's result against NCCL and against the full batch on one GPU (every rank takes part)
+            dp_check = dp_check_block(ctx, wl, comm, dist, world, rank, X, T, Ws, bs, shard, overlap)
+        except Exception as e:
+            dp_check = {"error": repr(e)}
+    if not args.headline_only:
+        if world > 1:
+            secondary["hvp"] = hvp_metric(ctx, ext, torch, wl, comm, world, rank, pk, dist)
+            try:
+                secondary["batched_tape"] = batched_metric(ctx, torch, gb, wl, pk, world, rank, dist)[0]
+            except Exception as e:
+                secondary["batched_tape"] = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    pk = peaks()
-    # TF32 dense = half of the measured bf16 figure. MEASURED_PEAKS.json has two: a burst (clocks at max) and a
-    # sustained one (seconds under the power cap, ~1.3 GHz). The denominator is the one whose clock regime the timed
-    # region was in, by the SM clocks sampled during it; both fractions are reported.
-    burst_regime = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.9 * clocks["sm_max_mhz"])
-    peak_key = "bf16_tflops" if burst_regime else "bf16_tflops_sustained"
-    tf32_peak = pk[peak_key] / 2.0
+    # TF32 dense peak = half of the measured bf16 figure. The timed region is a fraction of a second of GEMMs, so the
+    # denominator is the BURST figure of MEASURED_PEAKS.json, always; the sustained one (seconds under the power cap) is a
+    # side field. (r01 switched between the two on the sampled clock, which gave one kernel two fractions.)
+    tf32_peak = pk["bf16_tflops"] / 2.0
     gemm = prof["matmul"]
     gemm_ms = gemm["ms"] / max(1, gemm["launches"])
     logical_flop = 2.0 * rows * D * D
-    tc_path = os.environ.get("GADCU_GEMM_PATH", "auto")
     mma_flop = 3.0 * logical_flop  # 3xTF32: three tensor-core products per logical product
     achieved = mma_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic, traffic_source = ncu_traffic_entry("gemm_tf32x3_pair_kernel")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-                "traffic": ncu_traffic("gemm_tf32x3_pair_kernel"), "kernel": "gemm_tf32x3_pair_kernel + its operand splits (fwd / dA / dW), 3xTF32",
-                "frac_of_burst_peak": achieved / (pk["bf16_tflops"] / 2.0), "frac_of_sustained_peak": achieved / (pk["bf16_tflops_sustained"] / 2.0),
+                "traffic": traffic if world == 1 else None, "traffic_source": traffic_source if world == 1 else None,
+                "kernel": "gemm_tf32x3_pair_kernel (fwd / dA / dW) incl. whatever operand preparation runs as separate launches, 3xTF32",
+                "frac_of_sustained_peak": achieved / (pk["bf16_tflops_sustained"] / 2.0),
                 "logical_fp32_tflops": logical_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
-                "peak_source": f"{pk['source']}: {peak_key}/2 (sampled SM clock {'at' if burst_regime else 'below'} max)", "avg_launch_ms": gemm_ms, "launches": gemm["launches"],
-                "share_of_step": gemm["ms"] / ms if ms > 0 else None, "gemm_path": tc_path}
+                "peak_source": f"{pk['source']}: bf16_tflops/2 (burst figure; TF32 dense = half of bf16 dense)", "avg_launch_ms": gemm_ms,
+                "launches": gemm["launches"], "flop_per_launch": mma_flop, "share_of_step": gemm["ms"] / ms if ms > 0 else None}
 
     line = {"metric": "MLP fwd+bwd steps/s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C4 3-layer tanh MLP {D}-wide, batch {B_TOTAL}, f32, Graph1 fwd + reverse sweep", "global_batch": B_TOTAL,
-                       "rows_per_gpu": rows, "parallelism": f"dp{world} (batch rows sharded, NCCL allreduce of weight grads" + (": dW GEMM epilogues reduce-scatter over NVLink peer memory, gather overlapped with the sweep)" if overlap and world > 1 else ")"),
+                       "rows_per_gpu": rows, "parallelism": f"dp{world} (batch rows sharded, weight gradients summed over ranks" + (": dW GEMMs feed a reduce-scatter / all-gather over NVLink peer memory overlapped with the sweep)" if overlap and world > 1 else ")"),
                        "l2": "inputs larger than L2 (activations 128 MiB, weights 64 MiB each vs 126 MB L2)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "kernel_time_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}, "host_issue_ms_per_step": host_issue_ms,
             "loss": loss_val}
+    if dp_check is not None:
+        line["dp_check"] = dp_check
 
-    if hvp_multi is not None:
-        line["secondary"] = {"hvp": hvp_multi}
     if world == 1 and not args.headline_only:
         try:
-            line["secondary"] = secondary_metrics(ctx, ext, torch, gb, wl, pk, args)
+            secondary = secondary_metrics(ctx, ext, torch, gb, wl, pk, args)
         except Exception as e:  # the headline line must survive
-            line["secondary"] = {"error": repr(e)}
+            secondary = {"error": repr(e)}
         try:
-            threads = host_cores()
-            rows_s = 1024  # ~10 s of CPU work on 16 cores: one eighth of the batch at full width, all L layers
-            v, t = cpu_mlp_steps_per_s(rows_s, threads)
-            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "seconds": t,
-                                    "sample": f"{rows_s} of {B_TOTAL} batch rows at full width D={D}, L={L}; scaled by {B_TOTAL // rows_s}x"}
+            line["cpu_baseline"], line["parity"] = cpu_baseline_and_parity(ctx, wl, X, T, Ws, bs, keep["out"])
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
+    if secondary:
+        line["secondary"] = secondary
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
+def cpu_baseline_and_parity(ctx, wl, X, T, Ws, bs, device_out):
+    """The CPU port on the SAME inputs as the device step (read back from the device), all host cores, at the full batch
+    when that is about half a minute of CPU work or less, else on the first `rows` rows (then the device recomputes that
+    shard for the comparison). One run gives both the reported baseline and the parity error of this line."""
+    oracle_py = oracle_module()
+    threads = host_cores()
+    gemm = cpu_gemm_kind(oracle_py, threads)
+    hW = [w.numpy()[:, :, 0, 0] for w in Ws]
+    hb = [b.numpy()[:, :, 0, 0] for b in bs]
+    hX, hT = X.numpy()[:, :, 0, 0], T.numpy()[:, :, 0, 0]
+    t_cal, _ = cpu_mlp_step_seconds(oracle_py, 512, threads, (np.ascontiguousarray(hX[:512]), hW, hb, np.ascontiguousarray(hT[:512])))
+    rows = B_TOTAL
+    while rows > 1024 and t_cal * (rows / 512.0) > 30.0:
+        rows //= 2
+    data = (np.ascontiguousarray(hX[:rows]), hW, hb, np.ascontiguousarray(hT[:rows]))
+    secs, (oloss, ogW, ogb) = cpu_mlp_step_seconds(oracle_py, rows, threads, data)
+    scale = B_TOTAL // rows
+    if rows == B_TOTAL:
+        dloss, dgW, dgb = device_out
+    else:
+        dloss, dgW, dgb = wl.mlp_step(ctx, ctx.array(data[0]), Ws, bs, ctx.array(data[3]))
+    per_array = {f"dW{l + 1}": rel_err(dgW[l].numpy()[:, :, 0, 0], ogW[l]) for l in range(L)}
+    per_array.update({f"db{l + 1}": rel_err(dgb[l].numpy()[:, :, 0, 0], ogb[l]) for l in range(L)})
+    parity = {"max_rel": max(per_array.values()), "vs": "oracle", "per_array": per_array, "loss_rel": abs(dloss.item() - oloss) / abs(oloss),
+              "rows": rows, "what": "max |device - oracle| / max |oracle| over every dL/dW_l and dL/db_l of one step on the same inputs; both are f32 "
+              "computations with different summation orders (3xTF32 tensor-core tiles vs a CPU sgemm), so this is f32 rounding of sums over "
+              f"{rows} rows, not a bit comparison"}
+    cpu = {"value": 1.0 / (secs * scale), "unit": "steps/s", "cores": threads, "kind": "port", "seconds": secs, "gemm": gemm,
+           "sample": f"{rows} of {B_TOTAL} batch rows at full width D={D}, L={L}, the device's own inputs" + ("" if scale == 1 else f"; scaled by {scale}x")}
+    return cpu, parity
+
+
+def dp_check_block(ctx, wl, comm, dist, world, rank, X, T, Ws, bs, shard, overlap):
+    """Untimed correctness of the N-GPU step at the bench's own shard shape (rows = 8192 / N, D = 4096):
+      * the fused exchange against one grouped NCCL all-reduce of the same local gradients (bit-equal at 2 ranks when no GEMM
+        split its k range: a + b is the same in either order; beyond that the association differs);
+      * against the full batch evaluated on rank 0 alone, shard by shard with the gradients added up on that one GPU."""
+    a = wl.mlp_step(ctx, X, Ws, bs, T, comm, overlap)
+    b = wl.mlp_step(ctx, X, Ws, bs, T, comm, False)
+    a_np = [g.numpy() for g in a[1] + a[2]]
+    b_np = [g.numpy() for g in b[1] + b[2]]
+    names = [f"dW{l + 1}" for l in range(L)] + [f"db{l + 1}" for l in range(L)]
+    out = {"rows_per_gpu": int(X.dims()[0]), "fused_vs_nccl_max_rel": max(rel_err(x, y) for x, y in zip(a_np, b_np)),
+           "fused_vs_nccl_bit_equal": bool(all(np.array_equal(x, y) for x, y in zip(a_np, b_np)) and a[0].item() == b[0].item())}
+    c = wl.mlp_step(ctx, X, Ws, bs, T, comm, overlap)
+    out["fused_repeatable"] = bool(all(np.array_equal(x, g.numpy()) for x, g in zip(a_np, c[1] + c[2])))
+    if rank == 0:
+        tot_loss, acc = 0.0, None
+        for r in range(world):
+            Xr, Tr = (X, T) if r == 0 else shard(r)
+            l_, gW, gb_ = wl.mlp_step(ctx, Xr, Ws, bs, Tr)
+            tot_loss += l_.item()
+            if acc is None:
+                acc = [g.clone() for g in gW + gb_]
+            else:
+                for dst, src in zip(acc, gW + gb_):
+                    dst.add_assign(src)
+        per = {n: rel_err(x, g.numpy()) for n, x, g in zip(names, a_np, acc)}
+        out["vs_full_batch_on_one_gpu"] = {"max_rel": max(per.values()), "per_array": per, "loss_rel": abs(a[0].item() - tot_loss) / abs(tot_loss)}
+    ctx.synchronize()
+    dist.barrier()
+    return out
+
+
+def batched_metric(ctx, torch, gb, wl, pk, world, rank, dist):
+    """C2: batched scalar tapes, 2^20 lanes x Rosenbrock-64, f64, one tape per lane; with N ranks the lanes are split evenly
+    and nothing is exchanged (independent units). `value` is what a gad program gets through the API: record the tape
+    (569 nodes), sweep, launch — every call, as the reference re-records its tape per example (net_ext.rs:52)."""
+    lanes_total, N = 1 << 20, 64
+    lanes = lanes_total // world
+    cols = [ctx.random((lanes,), 200 + i + 1000 * rank, dtype=gb.F64, a=-1.2, b=1.2) for i in range(N)]
+    res = {}
+
+    def batched():
+        res["r"] = wl.rosenbrock_batched_gradients(ctx, cols)
+
+    for _ in range(3):
+        batched()
+    ctx.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ctx.profile_begin()
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        batched()
+    ctx.synchronize()
+    wall = (time.perf_counter() - t0) / reps
+    prof = ctx.profile_end()
+    k_ms = prof["tile_transpose"]["ms"] / max(1, prof["tile_transpose"]["launches"])
+    if dist is not None:
+        t = torch.tensor([wall, k_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, k_ms = float(t[0].item()), float(t[1].item())
+    stats = res["r"][3].program_stats()
+    alg = 2 * N * 8  # bytes per gradient: read 64 f64, write 64 f64
+    kernel_gps = lanes_total / (k_ms * 1e-3) if k_ms > 0 else 0.0
+    traffic, traffic_source = ncu_traffic_entry("lane_program_c2")
+    # the same call sequence from a COMPILED host (examples/c2_host.c over include/gadcu.h: what a Rust gad program pays per step,
+    # without ctypes' microseconds per call), on this rank's GPU and this rank's columns; the slowest rank counts
+    compiled = None
+    exe = os.path.join(ROOT, "examples", "c2_host")
+    if os.path.exists(exe):
+        try:
+            ctx.synchronize()
+            r = subprocess.run([exe, str(ctx.device), str(lanes), "20", str(200 + 1000 * rank)], capture_output=True, text=True, timeout=300)
+            compiled = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-500:]}
+        except Exception as e:
+            compiled = {"error": repr(e)}
+        if compiled and "ms_per_call" in compiled:
+            grads = res["r"][2]
+            bits = np.uint64(0)
+            for c in grads:
+                bits = bits + c.numpy()[:4096, 0, 0, 0].view(np.uint64).sum(dtype=np.uint64)
+            compiled["same_bits_as_python_recorded"] = bool(int(bits) == int(compiled.pop("bits_checksum_first_4096_lanes")))
+            c_ms = compiled["ms_per_call"]
+            if dist is not None:
+                t = torch.tensor([c_ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                c_ms = float(t[0].item())
+            compiled["ms_per_call_max_over_ranks"] = c_ms
+            compiled["grads_per_s"] = lanes_total / (c_ms * 1e-3)
+    elif dist is not None:
+        pass
+    api_gps = compiled["grads_per_s"] if compiled and "grads_per_s" in compiled and "error" not in compiled else lanes_total / wall
+    out = {"metric": "batched-tape grads/s", "workload": f"C2 {lanes_total} lanes x Rosenbrock-{N}, f64, one tape per lane", "n_gpus": world,
+           "lanes_per_gpu": lanes, "value": api_gps, "unit": "grads/s",
+           "value_is": "API level: every call records the 569-node tape, sweeps it and launches (the tape is re-recorded per step, as the reference does: "
+                       "net_ext.rs:52)" + ("; host = compiled C over the C ABI (examples/c2_host.c)" if api_gps != lanes_total / wall else "; host = Python (ctypes)"),
+           "compiled_host": compiled, "python_host": {"ms_per_call": wall * 1e3, "grads_per_s": lanes_total / wall,
+                                                      "note": "the same calls through ctypes: ~1 100 calls x several microseconds of marshalling each"},
+           "kernel_ms": k_ms, "kernel_grads_per_s": kernel_gps, "scaling": "total lanes fixed, split evenly over the ranks, no collective" if world > 1 else None,
+           "program_instructions": stats["instructions"], "program_slots": stats["slots"],
+           "roofline": {"bound": "hbm", "achieved": kernel_gps * alg / 1e9 / world, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": kernel_gps * alg / 1e9 / world / pk["hbm_gbs"], "traffic": traffic if world == 1 else None,
+                        "traffic_source": traffic_source if world == 1 else None, "algorithmic_bytes_per_gradient": alg,
+                        "algorithmic_bytes": alg * lanes, "note": "per GPU: the lane kernel's algorithmic bytes / its CUDA-event time"}}
+    return out, res, cols
+
+
 def secondary_metrics(ctx, ext, torch, gb, wl, pk, args):
     out = {}
+    oracle_py = oracle_module()
 
     def ev_time(fn, reps):
         ctx.synchronize()
@@ -416,36 +614,32 @@ def secondary_metrics(ctx, ext, torch, gb, wl, pk, args):
     for _ in range(3):
         fwd_bwd()
     ms_fb = ev_time(fwd_bwd, 10)
+    traffic, traffic_source = ncu_traffic_entry("lane_program_c3_sweep")
     out["grad_sweep"] = {
         "metric": "grad-sweep HBM GB/s", "workload": "C3 64Mi-element exp/log/mul/add + sum, f32, reverse sweep", "value": gbs, "unit": "GB/s",
         "ms_per_sweep": ms_sweep, "launches_per_sweep": int(sweep_launches),
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                     "frac_of_8TBs": gbs / 8000.0, "traffic": ncu_traffic("lane_program_c3_sweep"), "algorithmic_bytes": alg_bytes,
+                     "frac_of_8TBs": gbs / 8000.0, "traffic": traffic, "traffic_source": traffic_source, "algorithmic_bytes": alg_bytes,
                      "note": "algorithmic = 4 passes (read x,y; write gx,gy); the per-node sweep materialises more (see DESIGN.md)"},
         "fwd_plus_sweep_ms": ms_fb, "fwd_plus_sweep_gbs": 6 * n * 4 / (ms_fb * 1e-3) / 1e9}
+    try:  # parity of this row: the oracle on a 2^22-element prefix of the same x, y (elementwise: prefix gradients do not depend on the rest)
+        m = 1 << 22
+        hx, hy = x.numpy().reshape(-1)[:m].copy(), y.numpy().reshape(-1)[:m].copy()
+        _, ogx, ogy, _, _ = oracle_py.c3(hx, hy)
+        dgx, dgy = keep["r"][1].numpy().reshape(-1)[:m], keep["r"][2].numpy().reshape(-1)[:m]
+        eps = float(np.finfo(np.float32).eps)
+        out["grad_sweep"]["parity"] = {"vs": "oracle", "elements": m,
+                                       "max_rel_dz_dy": float(np.max(np.abs(dgy - ogy) / np.abs(ogy))) / eps,
+                                       "max_err_dz_dx_in_eps_of_summands": float(np.max(np.abs(dgx.astype(np.float64) - ogx) / (np.abs(ogx.astype(np.float64) - 1.0) + 1.0))) / eps,
+                                       "unit": "f32 eps", "what": "dz/dy = exp(x)/y relative; dz/dx = exp(x) log(y) + 1 relative to |exp(x) log(y)| + 1 (the sum cancels); CUDA expf/logf vs glibc"}
+    except Exception as e:
+        out["grad_sweep"]["parity"] = {"error": repr(e)}
     del keep, g, vx, vy, z, x, y
 
-    # ---- C2: batched scalar tapes, 2^20 lanes x Rosenbrock-64, f64
+    # ---- C2
+    bt, res, cols = batched_metric(ctx, torch, gb, wl, pk, 1, 0, None)
     lanes, N = 1 << 20, 64
-    cols = [ctx.random((lanes,), 200 + i, dtype=gb.F64, a=-1.2, b=1.2) for i in range(N)]
-    res = {}
-
-    def batched():
-        res["r"] = wl.rosenbrock_batched_gradients(ctx, cols)
-
-    batched()
-    ctx.profile_begin()
-    t0 = time.perf_counter()
-    reps = 3
-    for _ in range(reps):
-        batched()
-    ctx.synchronize()
-    wall = (time.perf_counter() - t0) / reps
-    prof = ctx.profile_end()
-    k_ms = prof["tile_transpose"]["ms"] / max(1, prof["tile_transpose"]["launches"])
-    stats = res["r"][3].program_stats()
-    gps = lanes / (k_ms * 1e-3) if k_ms > 0 else 0.0
-    # steady state of an optimiser loop: the same tapes at new points through the compiled program (no re-recording)
+    # steady state of an optimiser loop that keeps the store: the same tapes at new points through the compiled program
     store = res["r"][3]
     cols2 = [ctx.random((lanes,), 300 + i, dtype=gb.F64, a=-1.2, b=1.2) for i in range(N)]
     for _ in range(3):  # (the first calls grow the pool by a second set of output columns)
@@ -456,18 +650,21 @@ def secondary_metrics(ctx, ext, torch, gb, wl, pk, args):
         keep_r = store.rerun(cols2)
     ctx.synchronize()
     rerun_wall = (time.perf_counter() - t0) / 10
-    alg = 2 * N * 8  # bytes per gradient: read 64 f64, write 64 f64
-    out["batched_tape"] = {
-        "metric": "batched-tape grads/s", "workload": f"C2 {lanes} lanes x Rosenbrock-{N}, f64, one tape per lane", "value": gps,
-        "unit": "grads/s", "kernel_ms": k_ms, "end_to_end_ms_incl_tape_build": wall * 1e3, "end_to_end_grads_per_s": lanes / wall,
-        "rerun_ms_wall": rerun_wall * 1e3, "rerun_grads_per_s_wall": lanes / rerun_wall,
-        "program_instructions": stats["instructions"], "program_slots": stats["slots"],
-        "roofline": {"bound": "hbm", "achieved": gps * alg / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": gps * alg / 1e9 / pk["hbm_gbs"], "traffic": ncu_traffic("lane_program_c2"),
-                     "algorithmic_bytes_per_gradient": alg, "algorithmic_bytes": alg * lanes}}
-    del cols, res
+    bt["rerun_ms_wall"] = rerun_wall * 1e3
+    bt["rerun_grads_per_s_wall"] = lanes / rerun_wall
+    try:  # parity of this row: sampled lanes against the oracle's scalar tape, bit for bit
+        idx = np.random.default_rng(0).choice(lanes, 1024, replace=False)
+        hx = np.stack([c.numpy()[:, 0, 0, 0][idx] for c in cols])
+        got = np.stack([c.numpy()[:, 0, 0, 0][idx] for c in res["r"][2]])
+        _, og, _ = oracle_py.rosenbrock_batch(hx, nthreads=host_cores())
+        bt["parity"] = {"vs": "oracle", "lanes_sampled": int(idx.size), "max_ulp": 0 if np.array_equal(got, og) else int(np.max(np.abs(got.view(np.int64) - og.view(np.int64)))),
+                        "bit_identical": bool(np.array_equal(got, og))}
+    except Exception as e:
+        bt["parity"] = {"error": repr(e)}
+    out["batched_tape"] = bt
+    del cols, res, cols2, keep_r, store
 
-    out["hvp"] = hvp_metric(ctx, ext, torch, wl, None, 1, 0)
+    out["hvp"] = hvp_metric(ctx, ext, torch, wl, None, 1, 0, pk)
     try:  # launch-bound sizes: the same step eager and as ONE replayed CUDA graph (gadcu_capture_*, north-star subsystem 1)
         out["graph_replay"] = replay_metric(ctx, ext, torch, gb, wl)
     except Exception as e:
@@ -541,9 +738,12 @@ def replay_metric(ctx, ext, torch, gb, wl):
     return res
 
 
-def hvp_metric(ctx, ext, torch, wl, comm, world, rank, dist=None):
+def hvp_metric(ctx, ext, torch, wl, comm, world, rank, pk, dist=None):
     """C5: Hessian-vector products/s of the MLP loss on GraphN (reverse over reverse), C4 shapes, rows sharded over
-    the ranks and the products all-reduced. Every rank runs it; rank 0 reports."""
+    the ranks and the products summed over them as the second sweep completes each. Every rank runs it; rank 0 reports.
+    The reference's own matmul VJP (matrix.rs:164-176) cannot produce this workload for B != D — it is a Dimensions error
+    for the transposed operands of the recorded backward GEMMs — so what runs here is the library's default (corrected
+    adjoint) mode, and the CPU figure beside it is the oracle with the same switch."""
     try:
         rows = B_TOTAL // world
         X = ctx.random((rows, D), 5 + 100 * rank, normal=True, a=0.0, b=1.0)
@@ -561,26 +761,63 @@ def hvp_metric(ctx, ext, torch, wl, comm, world, rank, dist=None):
         ctx.synchronize()
         if dist is not None:
             dist.barrier()
+        reps = 5
         ctx.profile_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
-        for _ in range(5):
+        for _ in range(reps):
             hvp()
         e1.record(ext)
         e1.synchronize()
-        ms_hvp = e0.elapsed_time(e1) / 5
+        ms_hvp = e0.elapsed_time(e1) / reps
         prof = ctx.profile_end()
         if dist is not None:
             t = torch.tensor([ms_hvp], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_hvp = float(t.item())
-        gemms = prof["matmul"]["launches"] / 5
-        return {"metric": "MLP loss Hessian-vector products/s", "workload": f"C5 GraphN reverse-over-reverse, B={B_TOTAL}, D={D}, L={L}, f32",
-                "value": 1000.0 / ms_hvp, "unit": "HVPs/s", "n_gpus": world, "ms_per_hvp": ms_hvp, "tape_nodes": int(hv["r"][2]),
-                "gemms_per_hvp": gemms, "logical_tflop_per_hvp": gemms * 2.0 * B_TOTAL * D * D / 1e12,
-                "gemm_ms_per_hvp_per_gpu": prof["matmul"]["ms"] / 5}
+        gemms = prof["matmul"]["launches"] / reps
+        gemm_ms = prof["matmul"]["ms"] / max(1, prof["matmul"]["launches"])
+        mma_flop = 3.0 * 2.0 * rows * D * D  # per GEMM launch: every product of both sweeps is [rows or D] x D x [D or rows]
+        achieved = mma_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        out = {"metric": "MLP loss Hessian-vector products/s", "workload": f"C5 GraphN reverse-over-reverse, B={B_TOTAL}, D={D}, L={L}, f32",
+               "value": 1000.0 / ms_hvp, "unit": "HVPs/s", "n_gpus": world, "ms_per_hvp": ms_hvp, "tape_nodes": int(hv["r"][2]),
+               "gemms_per_hvp": gemms, "logical_tflop_per_hvp": gemms * 2.0 * B_TOTAL * D * D / 1e12,
+               "gemm_ms_per_hvp_per_gpu": prof["matmul"]["ms"] / reps,
+               "kernel_time_ms_per_hvp": {k: v["ms"] / reps for k, v in prof.items()},
+               "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"] / 2.0, "unit": "TFLOP/s",
+                            "frac": achieved / (pk["bf16_tflops"] / 2.0), "traffic": None, "avg_launch_ms": gemm_ms,
+                            "flop_per_launch": mma_flop, "share_of_hvp": prof["matmul"]["ms"] / reps / ms_hvp,
+                            "kernel": "gemm_tf32x3_pair_kernel, the same kernel as the headline (3xTF32 MMA flop / CUDA-event time of the GEMM launches)"},
+               "note": "the reference's matmul VJP cannot differentiate through its own backward GEMMs for B != D (gad/src/matrix.rs:164-176: "
+                       "Dimensions error for transposed operands); measured in the library's default corrected-adjoint mode"}
+        if world == 1 and rank == 0:
+            try:
+                out["cpu_baseline"], out["parity"] = hvp_cpu_baseline_and_parity(ctx, wl, X, T, Ws, bs, vs)
+            except Exception as e:
+                out["cpu_baseline"] = {"error": repr(e)}
+        return out
     except Exception as e:
         return {"error": repr(e)}
+
+
+def hvp_cpu_baseline_and_parity(ctx, wl, X, T, Ws, bs, vs):
+    """The oracle's GraphN with the corrected adjoint on the first 1024 rows of the device's own inputs (all host cores,
+    sgemm through the host's BLAS when there is one), timed; the device recomputes that shard for the comparison."""
+    oracle_py = oracle_module()
+    threads = host_cores()
+    gemm = cpu_gemm_kind(oracle_py, threads)
+    rows = 1024
+    hX, hT = np.ascontiguousarray(X.numpy()[:rows, :, 0, 0]), np.ascontiguousarray(T.numpy()[:rows, :, 0, 0])
+    hW, hb, hv_ = [w.numpy()[:, :, 0, 0] for w in Ws], [b.numpy()[:, :, 0, 0] for b in bs], [v.numpy()[:, :, 0, 0] for v in vs]
+    oloss, ohv, secs, nodes = oracle_py.mlp_hvp(hX, hW, hb, hT, hv_, nthreads=threads)
+    dhv, dloss, dnodes = wl.mlp_hvp(ctx, ctx.array(hX), Ws, bs, ctx.array(hT), vs)
+    per = {f"Hv{l + 1}": rel_err(dhv[l].numpy()[:, :, 0, 0], ohv[l]) for l in range(L)}
+    scale = B_TOTAL // rows
+    cpu = {"value": 1.0 / (secs * scale), "unit": "HVPs/s", "cores": threads, "kind": "port", "seconds": secs, "gemm": gemm,
+           "sample": f"{rows} of {B_TOTAL} batch rows at full width, the device's own inputs; scaled by {scale}x; oracle GraphN with the corrected matmul adjoint"}
+    parity = {"max_rel": max(per.values()), "vs": "oracle (corrected adjoint)", "per_array": per, "loss_rel": abs(dloss.item() - oloss) / abs(oloss),
+              "rows": rows, "tape_nodes_equal": bool(int(dnodes) == int(nodes))}
+    return cpu, parity
 
 
 def main():

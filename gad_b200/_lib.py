@@ -77,6 +77,7 @@ SIGNATURES = {
     "gadcu_array_upload": (C.c_int, [P, P, P]),
     "gadcu_array_upload_async": (C.c_int, [P, P]),
     "gadcu_ctx_wait_uploads": (C.c_int, [P]),
+    "gadcu_array_clone": (C.c_int, [P, PP]),
     "gadcu_array_retain": (C.c_int, [P]),
     "gadcu_array_release": (C.c_int, [P]),
     "gadcu_array_dims": (C.c_int, [P, DP]),
@@ -115,6 +116,7 @@ SIGNATURES = {
     "gadcu_store_add_gradient": (C.c_int, [P, P, C.c_uint32, C.c_uint32, VP]),
     "gadcu_evaluate_gradients": (C.c_int, [P, C.c_uint32, C.c_uint32, P, C.c_int, PP]),
     "gadcu_compute_gradients": (C.c_int, [P, C.c_uint32, C.c_uint32, VP, PP]),
+    "gadcu_compute_gradients_dp": (C.c_int, [P, C.c_uint32, C.c_uint32, VP, P, PP]),
     "gadcu_store_get": (C.c_int, [P, C.c_uint32, C.c_uint32, VP, C.POINTER(C.c_int)]),
     "gadcu_store_ids": (C.c_size_t, [P, C.POINTER(C.c_uint32), C.c_size_t]),
     "gadcu_store_destroy": (C.c_int, [P]),

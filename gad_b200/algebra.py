@@ -219,8 +219,10 @@ class CuArray:
         self.handle = handle
 
     def clone(self) -> "CuArray":
-        _check(self.ctx.lib.gadcu_array_retain(self.handle))
-        return CuArray(self.ctx, C.c_void_p(self.handle.value))
+        """af::Array::clone: a new handle on the same buffer (O(1)); `add_assign` on either leaves the other alone."""
+        h = C.c_void_p()
+        _check(self.ctx.lib.gadcu_array_clone(self.handle, C.byref(h)))
+        return CuArray(self.ctx, h)
 
     def dims(self) -> tuple:
         d = Dim4()
@@ -651,9 +653,14 @@ class GraphN(_DeviceAlgebra):
     """lib.rs:532 — higher-order tape; gradients are values recorded on the tape."""
     KIND = 3
 
-    def compute_gradients(self, gid: GradientId, gradient: Value) -> Store:  # graph.rs:307-318
+    def compute_gradients(self, gid: GradientId, gradient: Value, comm: Optional["Comm"] = None) -> Store:  # graph.rs:307-318
+        """With `comm`: the sweep of one batch shard — every variable's gradient is summed over the ranks as soon as the
+        sweep has completed it (gadcu_compute_gradients_dp) and comes back as a constant value."""
         h = C.c_void_p()
-        _check(self.lib.gadcu_compute_gradients(self.handle, gid.arena, gid.index, C.byref(gradient._c()), C.byref(h)))
+        if comm is not None and comm.nranks > 1:
+            _check(self.lib.gadcu_compute_gradients_dp(self.handle, gid.arena, gid.index, C.byref(gradient._c()), comm.handle, C.byref(h)))
+        else:
+            _check(self.lib.gadcu_compute_gradients(self.handle, gid.arena, gid.index, C.byref(gradient._c()), C.byref(h)))
         return Store(self.ctx, h, values=True)
 
     def make_node(self, data: CuArray, inputs: Sequence[Value], vjp) -> Value:

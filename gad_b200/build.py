@@ -73,5 +73,28 @@ def build(force: bool = False, verbose: bool = True) -> str:
     return LIB
 
 
+def build_examples(verbose: bool = True) -> list:
+    """Compile the stand-alone C hosts under examples/ against the built library (gcc; they only run on a GPU box).
+    examples/c2_host is what bench.py times for the API-level batched-tape figure: a compiled host recording its tape
+    through the C ABI every step, as a Rust gad program would."""
+    out = []
+    lib_dir = os.path.relpath(LIBDIR, os.path.join(ROOT, "examples"))
+    for name in ("c2_host",):
+        src, exe = os.path.join(ROOT, "examples", name + ".c"), os.path.join(ROOT, "examples", name)
+        if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+            out.append(exe)
+            continue
+        cmd = [os.environ.get("CC", "gcc"), "-O2", "-Wall", src, "-I", os.path.join(ROOT, "include"), "-L", LIBDIR, "-lgadcu",
+               "-Wl,-rpath,$ORIGIN/" + lib_dir, "-o", exe]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"building {name} failed:\n{res.stdout}\n{res.stderr}")
+        if verbose:
+            print(f"built {exe}")
+        out.append(exe)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv)
+    build_examples()

@@ -331,7 +331,9 @@ class GraphAlgebra final : public Algebra {
   // Called during a Graph1 sweep with each VARIABLE's gradient as soon as no unprocessed node can contribute to it
   // any more (and, at the end, for the variables the sweep never completed): the data-parallel sweep starts the
   // all-reduce of a layer's weight gradient while the layers below are still being differentiated.
-  using FinalHook = std::function<void(Id, const ArrayRef&)>;
+  // The hook may return a replacement array for the store entry (a private copy it will write into, when the gradient's
+  // buffer is visible outside the store — the caller's seed, an array stored under several ids); null keeps the entry.
+  using FinalHook = std::function<ArrayRef(Id, const ArrayRef&)>;
   void set_final_hook(FinalHook h) { final_hook_ = std::move(h); }
   // Asked by the matmul VJP when the product it is about to compute is the ONLY contribution to a variable's
   // gradient: may compute it itself (the data-parallel GEMM whose epilogue reduce-scatters over NVLink) and return

@@ -89,6 +89,7 @@ struct SymProgram {
   std::vector<ArrayRef> launch_compiled(const Compiled& c, size_t nout);
   std::map<std::tuple<uint16_t, int32_t, int32_t, int32_t, int32_t, double>, int32_t> value_number;  // array mode: CSE
   uint64_t last_instructions = 0, last_slots = 0;
+  bool retired = false;      // one of its leaf buffers has been overwritten in place: closed for new instructions (lazy_before_write)
   std::mutex mu;
 
   int32_t emit(SymInstr i) {
@@ -739,12 +740,61 @@ std::vector<ArrayRef> SymProgram::launch_compiled(const Compiled& c, size_t nout
   return out_cols;
 }
 
+// ---- plans by tape structure ------------------------------------------------------------------------------------
+// A gad program re-records its tape every step (net_ext.rs:52), so every step brings a NEW SymProgram with the same
+// instruction stream as the last one. Dead-code elimination, list scheduling and building the kernel's structural key
+// for a thousand-instruction tape cost far more than recording it; they depend on nothing but the recorded stream, the
+// requested outputs and a few shape facts — so finished plans are kept process-wide under exactly that, and a later tape
+// with the same structure goes from "sweep recorded" to "kernel launched" with one hash of its stream.
+struct PlanKey {
+  std::vector<uint64_t> words;
+  uint64_t hash = 0;
+  bool operator==(const PlanKey& o) const { return hash == o.hash && words == o.words; }
+};
+struct PlanKeyHash { size_t operator()(const PlanKey& k) const { return size_t(k.hash); } };
+std::mutex g_plans_mu;
+std::unordered_map<PlanKey, SymProgram::Compiled, PlanKeyHash> g_plans;
+
+PlanKey plan_key(const SymProgram& P, const std::vector<int32_t>& todo) {
+  PlanKey k;
+  k.words.reserve(P.instrs.size() * 4 + todo.size() + 4);
+  bool aligned = true;
+  for (const ArrayRef& in : P.inputs) aligned = aligned && (reinterpret_cast<uintptr_t>(in->ptr()) & 15) == 0;
+  k.words.push_back(uint64_t(P.dtype) | uint64_t(P.lanes % 4) << 8 | uint64_t(P.lanes < (1ull << 32)) << 16 | uint64_t(aligned) << 17 |
+                    uint64_t(P.instrs.size()) << 32);
+  for (const SymInstr& I : P.instrs) {
+    k.words.push_back(uint64_t(I.op) | uint64_t(uint32_t(I.a)) << 16);
+    k.words.push_back(uint64_t(uint32_t(I.b)) | uint64_t(uint32_t(I.c)) << 32);
+    uint64_t bits;
+    std::memcpy(&bits, &I.imm, 8);
+    k.words.push_back(uint64_t(uint32_t(I.d)) ^ (bits * 0x9E3779B97F4A7C15ull));
+    k.words.push_back(bits);
+  }
+  for (int32_t r : todo) k.words.push_back(uint64_t(uint32_t(r)) | 1ull << 40);
+  uint64_t h = 1469598103934665603ull;
+  for (uint64_t w : k.words) { h ^= w; h *= 1099511628211ull; }
+  k.hash = h;
+  return k;
+}
+
 std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   const int32_t n = int32_t(instrs.size());
   const bool reusable = !array_mode && cache.empty();
+  PlanKey pkey;
   if (reusable) {
     auto it = compiled.find(todo);
     if (it != compiled.end()) return launch_compiled(it->second, todo.size());
+    static const bool plans_on = [] { const char* e = getenv("GADCU_PLAN_CACHE"); return !e || atoi(e) != 0; }();
+    if (plans_on) {
+      pkey = plan_key(*this, todo);
+      bool hit = false;
+      {
+        std::lock_guard<std::mutex> lk(g_plans_mu);
+        auto g = g_plans.find(pkey);
+        if (g != g_plans.end()) { compiled[todo] = g->second; hit = true; }
+      }
+      if (hit) return launch_compiled(compiled[todo], todo.size());
+    }
   }
   auto is_load = [](uint16_t op) { return op == S_LOAD || op == S_LOADU || op == S_LOADCOL || op == S_LOADROW; };
   // 1. what the requested outputs depend on; a register that already has a materialised column is a leaf
@@ -1014,6 +1064,11 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
     c.stage_blocks = J.stage_blocks;
     c.instructions = last_instructions;
     c.values = last_slots;
+    if (!pkey.words.empty()) {
+      std::lock_guard<std::mutex> lk(g_plans_mu);
+      if (g_plans.size() >= 256) g_plans.clear();  // (a process that keeps inventing tape structures: start over)
+      g_plans[pkey] = c;
+    }
     compiled[todo] = std::move(c);
   }
   // 4. outputs + parameter block (layout of `struct P`: every field is 8 bytes wide)
@@ -1185,6 +1240,7 @@ std::shared_ptr<SymProgram> lazy_program(gadcu_ctx* ctx, gadcu_dtype dt, uint64_
   prog->array_mode = true;
   prog->epoch = epoch;
   ctx->lazy_programs[key] = prog;
+  ctx->lazy_all.emplace_back(prog);
   return prog;
 }
 
@@ -1292,12 +1348,24 @@ ArrayRef lazy_elementwise(gadcu_ctx* ctx, k::EwOp op, const ArrayRef& acc, const
 }
 
 // Before `buffer` is overwritten in place (WeightOps::add_assign, an upload, an all-reduce): compute every value
-// that still has a handle and would read the old contents later.
+// that still has a handle and would read the old contents later — in EVERY program that can still be asked for
+// values (the open ones and those of earlier tapes that live on through their handles). A program that loads the
+// buffer is then RETIRED: it leaves the table of open programs, so nothing recorded after the write is appended to it.
+// That is what keeps later ops honest: a new `exp(W)` opens a fresh program with a fresh load of W (no stale
+// register, no value-numbering hit on the pre-write `exp`), and a value forced here is only ever read back as the
+// bytes of its column (by another program), never recomputed from the overwritten leaf once its handle is gone.
 void lazy_before_write(gadcu_ctx* ctx, const void* buffer) {
   std::vector<std::shared_ptr<SymProgram>> progs;
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
-    for (auto& kv : ctx->lazy_programs) progs.push_back(std::static_pointer_cast<SymProgram>(kv.second));
+    size_t keep = 0;
+    for (auto& w : ctx->lazy_all) {
+      std::shared_ptr<void> p = w.lock();
+      if (!p) continue;
+      progs.push_back(std::static_pointer_cast<SymProgram>(p));
+      ctx->lazy_all[keep++] = w;
+    }
+    ctx->lazy_all.resize(keep);
   }
   for (auto& prog : progs) {
     std::vector<int32_t> todo;
@@ -1310,7 +1378,9 @@ void lazy_before_write(gadcu_ctx* ctx, const void* buffer) {
         const SymInstr& I = prog->instrs[r];
         if (I.op == S_LOAD || I.op == S_LOADU || I.op == S_LOADCOL || I.op == S_LOADROW) {
           dep[r] = prog->inputs[I.a]->ptr() == buffer;
-        } else if (I.op != S_CONST && !prog->cache.count(r)) {
+        } else if (I.op != S_CONST) {
+          // (true data dependence, also THROUGH registers that already have a column: such a column goes back to the
+          // pool with its last handle, and a live value above it would then be recomputed from the overwritten leaf)
           for (int32_t x : {I.a, I.b, I.c, I.d})
             if (x >= 0 && dep[x]) dep[r] = 1;
         }
@@ -1321,6 +1391,17 @@ void lazy_before_write(gadcu_ctx* ctx, const void* buffer) {
       if (!any) continue;
     }
     if (!todo.empty()) prog->run(todo);
+    {
+      // (a forced column may still go back to the pool with its last handle: nothing can be appended to a retired
+      // program, so no later instruction can ask for it to be recomputed from the overwritten leaf)
+      std::lock_guard<std::mutex> lk(prog->mu);
+      prog->retired = true;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto i = ctx->lazy_programs.begin(); i != ctx->lazy_programs.end();) {
+      if (i->second.get() == prog.get()) i = ctx->lazy_programs.erase(i);
+      else ++i;
+    }
   }
 }
 

@@ -99,11 +99,14 @@ gadcu_status gadcu_algebra_destroy(gadcu_algebra* alg) {
 gadcu_algebra_kind gadcu_algebra_get_kind(const gadcu_algebra* alg) { return alg->kind(); }
 size_t gadcu_algebra_num_nodes(const gadcu_algebra* alg) { return alg->num_nodes(); }
 
+// The algebra takes a CLONE of the caller's handle (core.rs:162-170 `variable(data: D)` takes the array by value; gad
+// programs pass `w.clone()`): what the tape and the returned Value hold is their own handle on the same buffer, so a
+// later `+=` on the caller's handle (WeightOps::add_assign, copy-on-write) cannot change what the tape recorded.
 gadcu_status gadcu_variable(gadcu_algebra* g, gadcu_array* data, gadcu_value* out) {
-  return guard([&] { out_value(out, g->variable(ArrayRef(data, true))); });
+  return guard([&] { out_value(out, g->variable(clone_handle(ArrayRef(data, true)))); });
 }
 gadcu_status gadcu_constant(gadcu_algebra* g, gadcu_array* data, gadcu_value* out) {
-  return guard([&] { out_value(out, g->constant(ArrayRef(data, true))); });
+  return guard([&] { out_value(out, g->constant(clone_handle(ArrayRef(data, true)))); });
 }
 gadcu_status gadcu_add_all(gadcu_algebra* g, const gadcu_value* const* vs, size_t n, gadcu_value* out) {
   return guard([&] {

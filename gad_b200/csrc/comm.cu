@@ -99,6 +99,7 @@ struct gadcu_comm {
   uint64_t small_calls = 0;       // small all-reduces so far (parity of the buffer)
   cudaEvent_t slot_done[kSlots] = {nullptr, nullptr, nullptr};
   std::vector<gadcu::ArrayRef> deferred;  // small gradients: one grouped NCCL all-reduce at the join
+  std::vector<std::pair<const gadcu_array*, gadcu::ArrayRef>> replaced;  // this sweep: gradient array -> the private copy reduced in its place
   bool no_peer_memory = false;    // CUDA IPC / peer access unavailable: everything goes through NCCL
   std::vector<std::pair<const char*, cudaEvent_t>> trace;  // GADCU_DP_TRACE=1: timeline of one step
 };
@@ -540,17 +541,42 @@ gadcu_status gadcu_evaluate_gradients_dp_with(gadcu_algebra* g, uint32_t arena, 
       return e && std::string(e) == "nccl-overlap" ? 1 : 0;
     }();
     if (dp) {
-      if (mode == 1) {
-        graph->set_final_hook([comm](Id, const ArrayRef& grad) { allreduce_async(comm, grad); });
-      } else {
-        graph->set_final_hook([comm](Id, const ArrayRef& grad) { comm->deferred.push_back(grad); });
+      // Every variable's gradient is reduced IN PLACE exactly once. ADD / SUB / ADDC / ADD_ALL hand the same array to
+      // several inputs (core.rs:227-232): the second id shares the first one's reduction instead of being summed over
+      // the ranks twice. A gradient whose buffer the caller can see (the seed itself, when the root is a variable; a
+      // lazy broadcast of it) is reduced in a private copy that replaces the store entry.
+      const Buffer* seed_buf = seed && seed->buf ? seed->buf.get() : nullptr;
+      graph->set_final_hook([comm, seed_buf](Id, const ArrayRef& grad_in) -> ArrayRef {
+        ArrayRef grad = grad_in;
+        if (grad->symbolic()) materialize(grad);
+        for (auto& r : comm->replaced)
+          if (r.first == grad.get()) return r.second;  // the same array under another id: shares the copy's reduction
+        for (auto& q : comm->deferred) {
+          if (q.get() == grad.get()) return ArrayRef();                       // same array under another id: queued already
+          if (q->buf.get() == grad->buf.get() && q->dims == grad->dims && !q->lazy() && !grad->lazy()) return q;
+        }
+        ArrayRef target = grad;
+        bool shared_buffer = grad->lazy() || grad->buf.get() == seed_buf;
+        for (auto& q : comm->deferred) shared_buffer = shared_buffer || q->buf.get() == grad->buf.get();  // (a view with other dims)
+        if (shared_buffer) {
+          ArrayRef dense = materialize(grad);
+          target = new_array(comm->ctx, dense->dtype, dense->dims, dense->is_scalar);
+          GADCU_CUDA(cudaMemcpyAsync(target->ptr(), dense->ptr(), dense->elements() * dense->elem_size(), cudaMemcpyDeviceToDevice, comm->ctx->stream));
+        }
+        comm->deferred.push_back(target);
+        if (target.get() != grad.get()) comm->replaced.emplace_back(grad.get(), target);
+        if (mode == 1) allreduce_async(comm, target);
+        return target.get() == grad_in.get() ? ArrayRef() : target;
+      });
+      if (mode != 1)
         graph->set_gemm_sink([comm](Id, const ArrayRef& lhs, const ArrayRef& rhs, MatProp pl, MatProp pr, bool last) { return dp_gemm(comm, lhs, rhs, pl, pr, last); });
-      }
     }
     auto finish = [&] {
       graph->set_final_hook(nullptr);
       graph->set_gemm_sink(nullptr);
       if (!dp) return;
+      comm->replaced.clear();
+      if (mode == 1) comm->deferred.clear();  // (already on their way, one all-reduce each)
       for (size_t i = 0; i < n_also; i++) comm->deferred.emplace_back(also[i], true);
       if (!comm->deferred.empty()) {
         std::vector<gadcu_array*> raw;
@@ -576,6 +602,42 @@ gadcu_status gadcu_evaluate_gradients_dp_with(gadcu_algebra* g, uint32_t arena, 
     finish();
     if (dp) mark(comm, "compute: joined", comm->ctx->stream);
     if (dp) dump_trace(comm);
+    *out = store.release();
+  });
+}
+
+// GraphN::compute_gradients (graph.rs:307-318) of one batch shard. The sweep records the backward pass on this rank's
+// tape as usual; every VARIABLE's gradient is, as soon as the sweep has completed it, copied and summed over the ranks on
+// the communicator's stream — overlapping the rest of the sweep — and the store hands out that sum as a CONSTANT (the
+// rank-summed array is not a node of this rank's tape; the recorded local gradient stays what later differentiation
+// sees). Joined before returning. comm == NULL or one rank: identical to gadcu_compute_gradients.
+gadcu_status gadcu_compute_gradients_dp(gadcu_algebra* g, uint32_t arena, uint32_t index, const gadcu_value* seed, gadcu_comm* comm,
+                                        gadcu_store** out) {
+  return guard([&] {
+    if (index == 0) fail(GADCU_ERR_MISSING_ID, "Trying to obtain `id` of a constant value.");
+    auto* graph = dynamic_cast<GraphAlgebra*>(g);
+    if (!graph || graph->kind() != GADCU_GRAPHN) fail(GADCU_ERR_INVALID, "compute_gradients_dp needs a GraphN algebra");
+    if (!seed) fail(GADCU_ERR_INVALID, "null seed");
+    const Value sv(ArrayRef(seed->data, true), Id{seed->arena, seed->index});
+    const bool dp = comm && comm->nranks > 1;
+    if (dp)
+      graph->set_final_hook([comm](Id, const ArrayRef& grad_in) -> ArrayRef {
+        ArrayRef dense = materialize(grad_in);
+        ArrayRef sum = new_array(comm->ctx, dense->dtype, dense->dims, dense->is_scalar);
+        GADCU_CUDA(cudaMemcpyAsync(sum->ptr(), dense->ptr(), dense->elements() * dense->elem_size(), cudaMemcpyDeviceToDevice, comm->ctx->stream));
+        allreduce_async(comm, sum);
+        return sum;
+      });
+    std::unique_ptr<Store> store;
+    try {
+      store = graph->compute_gradients(Id{arena, index}, sv);
+    } catch (...) {
+      graph->set_final_hook(nullptr);
+      if (dp) { try { join(comm); } catch (...) {} }
+      throw;
+    }
+    graph->set_final_hook(nullptr);
+    if (dp) join(comm);
     *out = store.release();
   });
 }

@@ -108,7 +108,10 @@ struct gadcu_ctx {
   // deferred elementwise regions (batched.cu): open lane programs by (element count, dtype)
   bool lazy = true;
   uint64_t lazy_threshold = 32768;  // smaller arrays run eagerly (one tiny kernel beats a specialised one)
-  std::map<std::pair<uint64_t, int>, std::shared_ptr<void>> lazy_programs;  // bumped by every new tape: scopes the TF32 split cache to one step
+  std::map<std::pair<uint64_t, int>, std::shared_ptr<void>> lazy_programs;  // the OPEN program per (elements, dtype): new ops are appended here
+  // every program that may still have live handles (open or not, this tape's or an earlier one's): what an in-place
+  // write into one of their leaf buffers has to walk (lazy_before_write). Expired entries are pruned on the way.
+  std::vector<std::weak_ptr<void>> lazy_all;
   void* pinned_scratch = nullptr;  // 4 KiB pinned staging for scalar reads
   void* dev_scratch = nullptr;     // reduction partials
   size_t dev_scratch_bytes = 0;
@@ -195,6 +198,7 @@ using ArrayRef = Ref<gadcu_array>;
 
 ArrayRef new_array(gadcu_ctx* ctx, gadcu_dtype dt, const Dim4& dims, bool is_scalar = false);
 ArrayRef view_array(const ArrayRef& src, const Dim4& dims, const Dim4& phys, bool is_scalar);
+ArrayRef clone_handle(const ArrayRef& src);  // a NEW handle on the same buffer (af::Array::clone): O(1), and what `+=` on one of them leaves alone
 ArrayRef materialize(const ArrayRef& a);  // dense copy of a lazy tile (identity for dense arrays)
 ArrayRef force_symbolic(const ArrayRef& a);  // batched.cu: run the lane program for this value
 

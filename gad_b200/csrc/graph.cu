@@ -563,6 +563,9 @@ void GraphAlgebra::vjp(const Node& n, Algebra& ga, Store& store, const Value& g)
       const bool fix1 = n.p1.transposed && !ctx->strict_reference;
       const bool fix2 = n.p2.transposed && !ctx->strict_reference;
       const MatProp T{true, false};
+      // matmul(W, W): both products feed the SAME variable. Neither is its whole gradient, so neither may be handed to
+      // the data-parallel sink (the second would be accumulated, unreduced, into a buffer the exchange is still writing)
+      const bool same_operand = v1.id.some() && v1.id == v2.id;
       if (v1.id.some()) {
         // operands and props of the product that yields dA
         const Value& lhs = fix1 ? v2 : g;
@@ -572,7 +575,7 @@ void GraphAlgebra::vjp(const Node& n, Algebra& ga, Store& store, const Value& g)
           auto it = store.values.find(v1.id);
           ArrayRef cur;
           if (it != store.values.end()) cur = std::move(it->second.data);
-          ArrayRef sunk = cur ? ArrayRef() : try_gemm_sink(v1.id, lhs.data, rhs.data, pl, pr);
+          ArrayRef sunk = (cur || same_operand) ? ArrayRef() : try_gemm_sink(v1.id, lhs.data, rhs.data, pl, pr);
           store.values[v1.id] = Value(sunk ? sunk : ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr));
         } else {
           Value l = fix1 ? ga.link(lhs) : lhs, r = fix1 ? rhs : ga.link(rhs);
@@ -588,7 +591,7 @@ void GraphAlgebra::vjp(const Node& n, Algebra& ga, Store& store, const Value& g)
           auto it = store.values.find(v2.id);
           ArrayRef cur;
           if (it != store.values.end()) cur = std::move(it->second.data);
-          ArrayRef sunk = cur ? ArrayRef() : try_gemm_sink(v2.id, lhs.data, rhs.data, pl, pr);
+          ArrayRef sunk = (cur || same_operand) ? ArrayRef() : try_gemm_sink(v2.id, lhs.data, rhs.data, pl, pr);
           store.values[v2.id] = Value(sunk ? sunk : ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr));
         } else {
           Value l = fix2 ? lhs : ga.link(lhs), r = fix2 ? ga.link(rhs) : rhs;
@@ -646,7 +649,9 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
   // final-gradient hook: how many nodes still have to run before a variable's gradient is complete
   // (member state is touched only by hooked — data-parallel — sweeps; plain evaluate_gradients(&self) stays re-entrant
   // from several threads, graph.rs:263-274)
-  const bool hooked = bool(final_hook_) && ga.is_eval();
+  // (Graph1: gradients are data. GraphN — the data-parallel compute_gradients — too: the hook sees the data of the
+  // recorded gradient value and answers with the array that replaces it in the store, as a constant)
+  const bool hooked = bool(final_hook_);
   std::vector<uint32_t> unhooked;
   std::vector<uint32_t>& waiting = hooked ? waiting_ : unhooked;  // by node index; only variables are counted
   if (hooked) {
@@ -707,7 +712,13 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
       for (uint32_t v : scratch)
         if (--waiting[v] == 0) {
           const Value* gv = store->get(Id{arena_id_, v});
-          if (gv && gv->data) { fired[v] = 1; if (!served_[v]) final_hook_(Id{arena_id_, v}, gv->data); }
+          if (gv && gv->data) {
+            fired[v] = 1;
+            if (!served_[v]) {
+              ArrayRef replacement = final_hook_(Id{arena_id_, v}, gv->data);
+              if (replacement) store->values[Id{arena_id_, v}] = Value(replacement);
+            }
+          }
         }
     }
     for (auto& in : node.inputs)
@@ -717,8 +728,10 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
   if (!waiting.empty())  // variables some unreached node also feeds (or the root itself): complete as far as this sweep goes
     for (auto& kv : store->values) {
       const Id vid = kv.first;
-      if (vid.arena == arena_id_ && vid.index < fired.size() && was_variable[vid.index] && !fired[vid.index] && !served_[vid.index] && kv.second.data)
-        final_hook_(vid, kv.second.data);
+      if (vid.arena == arena_id_ && vid.index < fired.size() && was_variable[vid.index] && !fired[vid.index] && !served_[vid.index] && kv.second.data) {
+        ArrayRef replacement = final_hook_(vid, kv.second.data);
+        if (replacement) kv.second = Value(replacement);
+      }
     }
   if (hooked) waiting_.clear();
   return store;

@@ -105,6 +105,19 @@ ArrayRef view_array(const ArrayRef& src_in, const Dim4& dims, const Dim4& phys, 
   return ArrayRef(a, false);
 }
 
+ArrayRef clone_handle(const ArrayRef& src) {
+  auto* a = new gadcu_array;
+  a->buf = src->buf;
+  a->dims = src->dims;
+  a->phys = src->phys;
+  a->dtype = src->dtype;
+  a->is_scalar = src->is_scalar;
+  a->ctx = src->ctx;
+  a->sym = src->sym;
+  a->sym_reg = src->sym_reg;
+  return ArrayRef(a, false);
+}
+
 ArrayRef materialize(const ArrayRef& a) {
   if (a->symbolic()) return force_symbolic(a);
   if (!a->lazy()) return a;
@@ -277,6 +290,9 @@ gadcu_status gadcu_array_to_host(const gadcu_array* a, void* host) {
   });
 }
 gadcu_status gadcu_array_retain(gadcu_array* a) { if (a) a->retain(); return GADCU_OK; }
+gadcu_status gadcu_array_clone(const gadcu_array* a, gadcu_array** out) {
+  return guard([&] { *out = clone_handle(ArrayRef(const_cast<gadcu_array*>(a), true)).detach(); });
+}
 gadcu_status gadcu_array_release(gadcu_array* a) { if (a) a->release(); return GADCU_OK; }
 gadcu_status gadcu_array_dims(const gadcu_array* a, gadcu_dim4* out) { *out = a->dims.c(); return GADCU_OK; }
 gadcu_dtype gadcu_array_dtype(const gadcu_array* a) { return a->dtype; }
@@ -317,28 +333,31 @@ gadcu_status gadcu_array_random(gadcu_ctx* ctx, gadcu_dtype dt, const gadcu_dim4
     *out = arr.detach();
   });
 }
-// net.rs:171-175: `*self += other` after check_equal_dimensions(other, self)
+// net.rs:171-175: `*self += other` after check_equal_dimensions(other, self). On an af::Array `+=` rebinds the handle
+// to a fresh array (arrays are copy-on-write values): clones taken earlier — get_weights() snapshots, the array the
+// user handed to set_weights, forward values a tape still holds — keep the old contents. So the sum is written in
+// place only when nobody else holds the buffer; otherwise it goes to a fresh buffer and THIS handle is rebound to it.
 gadcu_status gadcu_array_add_assign(gadcu_array* self, const gadcu_array* other) {
   return guard([&] {
     if (self->dims != other->dims) fail(GADCU_ERR_DIMENSIONS, "add_assign: " + other->dims.str() + " " + self->dims.str());
     if (self->dtype != other->dtype) fail(GADCU_ERR_TYPE, "add_assign: dtype mismatch");
     if (self->lazy()) fail(GADCU_ERR_INVALID, "add_assign into a lazy view");
     if (self->symbolic()) materialize(ArrayRef(self, true));
-    ArrayRef other_dense = other->symbolic() ? materialize(ArrayRef(const_cast<gadcu_array*>(other), true)) : ArrayRef(const_cast<gadcu_array*>(other), true);
-    other = other_dense.get();
+    ArrayRef other_dense = ArrayRef(const_cast<gadcu_array*>(other), true);
+    if (other_dense->symbolic() || (other_dense->lazy() && !other_dense->bcast1())) other_dense = materialize(other_dense);
+    // deferred elementwise values that would read `self` later are computed first, whether the bytes are about to be
+    // overwritten or the handle rebound (their programs hold this handle, not a copy of its pointer)
     lazy_before_write(self->ctx, self->ptr());
-    self->buf->mutated();
+    const bool shared = self->buf->refs.load() > 1;
+    ArrayRef fresh;
+    if (shared) fresh = new_array(self->ctx, self->dtype, self->dims, self->is_scalar);
+    else self->buf->mutated();
     k::EwArgs e;
-    e.dt = self->dtype; e.nin = 2; e.in[0] = self->ptr(); e.in[1] = other->ptr(); e.bcast[1] = other->bcast1();
-    if (other->lazy() && !other->bcast1()) {
-      ArrayRef dense = materialize(ArrayRef(const_cast<gadcu_array*>(other), true));
-      e.in[1] = dense->ptr();
-      e.out = self->ptr(); e.n = self->elements();
-      k::launch_ew(self->ctx, k::EwOp::ADD, e);
-      return;
-    }
-    e.out = self->ptr(); e.n = self->elements();
+    e.dt = self->dtype; e.nin = 2; e.in[0] = self->ptr(); e.in[1] = other_dense->ptr(); e.bcast[1] = other_dense->bcast1();
+    e.out = shared ? fresh->ptr() : self->ptr();
+    e.n = self->elements();
     k::launch_ew(self->ctx, k::EwOp::ADD, e);
+    if (shared) self->buf = fresh->buf;
   });
 }
 // net.rs:177-179: `self * lambda`

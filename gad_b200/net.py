@@ -26,17 +26,19 @@ from .algebra import CuArray, DimensionsError, EmptyError, LengthsError, Missing
 
 # ---- data helpers: a net's data is whatever the algebra's `variable` / `constant` accept --------------------------
 def dims_of(data) -> tuple:
-    """HasDims::dims (core.rs:41-73): Dim4 of an array, `()` of a scalar."""
+    """HasDims::dims (core.rs:41-73): Dim4 of an array, `()` of a scalar. Metadata only — nothing here computes."""
     if isinstance(data, CuArray):
         return () if data.is_scalar else data.dims()
     if isinstance(data, tuple):  # Check's values are dims
         return data
     if hasattr(data, "dims") and callable(data.dims):
         return data.dims()
-    arr = np.asarray(data)
-    if arr.ndim == 0:
+    shape = getattr(data, "shape", None)  # a host array handed in as input / target
+    if shape is None:
         return ()
-    shape = tuple(int(s) for s in arr.shape)
+    if len(shape) == 0:
+        return ()
+    shape = tuple(int(s) for s in shape)
     return shape + (1,) * (4 - len(shape))
 
 
@@ -51,25 +53,29 @@ def _check_equal_lengths(name: str, a: int, b: int) -> None:  # error.rs:156-167
 
 
 # ---- WeightOps over the nested weight structure (net.rs:100-104,161-180,483-493,559-569,600-616,686-704) ---------
+# A leaf is any array type with the reference's WeightOps surface — `scale(lambda) -> new`, `add_assign(other)` (in
+# place, copy-on-write), `clone()` — i.e. gad_b200's CuArray. No arithmetic happens in this module: the CPU tests run
+# the same nets on the oracle through an adapter of their own (tests/host_weights.py) that supplies such a type.
 def weights_scale(w, lam: float):
     if isinstance(w, (tuple, list)):
         return type(w)(weights_scale(x, lam) for x in w)
-    if isinstance(w, CuArray):
-        return w.scale(lam)
-    return np.asarray(w) * np.asarray(lam, dtype=np.asarray(w).dtype)
+    return w.scale(lam)
 
 
 def weights_add_assign(w, other):
-    """`self += other`, structure-wise; returns the updated structure (host arrays are values, device arrays are
-    updated in place like `af::Array += `)."""
+    """`self += other`, structure-wise (net.rs:171-175 per leaf); returns the structure."""
     if isinstance(w, (tuple, list)):
         _check_equal_lengths("add_assign", len(w), len(other))
         return type(w)(weights_add_assign(a, b) for a, b in zip(w, other))
-    if isinstance(w, CuArray):
-        w.add_assign(other)
-        return w
     _check_equal_dimensions("add_assign", dims_of(other), dims_of(w))
-    return np.asarray(w) + np.asarray(other).reshape(np.asarray(w).shape)  # (host arrays may carry trailing unit dims)
+    w.add_assign(other)
+    return w
+
+
+def weights_clone(w):
+    if isinstance(w, (tuple, list)):
+        return type(w)(weights_clone(x) for x in w)
+    return w.clone()
 
 
 def weights_leaves(w) -> list:
@@ -83,11 +89,17 @@ def weights_leaves(w) -> list:
 
 # ---- (de)serialisation of weights: checkpoint / resume (net.rs:100, tests/net.rs:136-149) ----------------------------
 _MAGIC = b"GADW1\0"
+_DT_CODE = {"float32": 0, "float64": 1}
+
+
+def _host(x):
+    """Host copy of a leaf as a numpy array shaped by its dims (column-major indexing preserved)."""
+    return x.numpy() if hasattr(x, "numpy") else np.asarray(x)
 
 
 def serialize_weights(w) -> bytes:
-    """Nested structure of arrays -> bytes. Layout: magic, then recursively: b'T'/b'L' + u32 count for tuples/lists,
-    b'A' + u8 dtype (0 f32, 1 f64) + 4 x u64 dims + raw column-major little-endian data for arrays."""
+    """Nested structure of arrays -> bytes, self-describing. Layout: magic, then recursively: b'T'/b'L' + u32 count for
+    tuples/lists, b'A' + u8 dtype (0 f32, 1 f64) + 4 x u64 dims + raw column-major little-endian data for arrays."""
     buf = io.BytesIO()
     buf.write(_MAGIC)
 
@@ -98,12 +110,12 @@ def serialize_weights(w) -> bytes:
             for y in x:
                 put(y)
             return
-        host = x.numpy() if isinstance(x, CuArray) else np.asarray(x)
-        if host.dtype not in (np.float32, np.float64):
+        host = _host(x)
+        if host.dtype.name not in _DT_CODE:
             raise TypeError(f"weights must be f32 or f64 arrays, got {host.dtype}")
         dims = dims_of(x) or (1, 1, 1, 1)
         buf.write(b"A")
-        buf.write(struct.pack("<B4Q", 0 if host.dtype == np.float32 else 1, *dims))
+        buf.write(struct.pack("<B4Q", _DT_CODE[host.dtype.name], *dims))
         buf.write(np.ascontiguousarray(host.reshape(-1, order="F")).astype(host.dtype.newbyteorder("<")).tobytes())
 
     put(w)
@@ -132,6 +144,80 @@ def deserialize_weights(data: bytes, ctx=None):
         return ctx.array(arr) if ctx is not None else arr
 
     return get()
+
+
+# The reference's own checkpoint format: `bincode::serialize(&net.get_weights())` (gad/tests/net.rs:136-149; bincode 1.3.1
+# per Cargo.lock, default options = little-endian fixed-width integers). Weights are nested tuples / `Vec`s of
+# `af::Array<T>`, whose serde impl is the `afserde` feature of the arrayfire crate 3.8.0 (gad/Cargo.toml:20): it
+# serialises `struct ArrayOnHost { dtype: DType, shape: Dim4, data: Vec<T> }`. Under bincode that is
+#     u32  variant index of af::DType (F32 = 0, F64 = 2)
+#     4 x u64  Dim4.dims
+#     u64  element count, then the elements in column-major order
+# tuples are the concatenation of their fields, `()` is zero bytes, a Vec is a u64 length followed by its items.
+# bincode is not self-describing, so reading needs the weight structure (`like`), exactly as Rust needs the type.
+# The arrayfire crate is not vendored under /root/reference and cannot be built here, so this layout is restated from
+# the published crate and is NOT checked against a blob written by the reference (unpinned); the round trip and the
+# byte layout above are what the tests pin.
+_AF_DTYPE = {"float32": 0, "float64": 2}
+
+
+def serialize_weights_bincode(w) -> bytes:
+    buf = io.BytesIO()
+
+    def put(x):
+        if isinstance(x, tuple):
+            for y in x:
+                put(y)
+            return
+        if isinstance(x, list):
+            buf.write(struct.pack("<Q", len(x)))
+            for y in x:
+                put(y)
+            return
+        host = _host(x)
+        if host.dtype.name not in _AF_DTYPE:
+            raise TypeError(f"weights must be f32 or f64 arrays, got {host.dtype}")
+        dims = dims_of(x) or (1, 1, 1, 1)
+        flat = np.ascontiguousarray(host.reshape(-1, order="F")).astype(host.dtype.newbyteorder("<"))
+        buf.write(struct.pack("<I4QQ", _AF_DTYPE[host.dtype.name], *dims, flat.size))
+        buf.write(flat.tobytes())
+
+    put(w)
+    return buf.getvalue()
+
+
+def deserialize_weights_bincode(data: bytes, like, ctx=None):
+    """`like`: a weight structure of the expected shape (e.g. `net.get_weights()` of a freshly built net) — the stand-in
+    for the Rust type that drives bincode's deserializer. Dtype, dims and length prefixes in the blob are checked."""
+    buf = io.BytesIO(data)
+
+    def take(n):
+        b = buf.read(n)
+        if len(b) != n:
+            raise ValueError("truncated bincode weight blob")
+        return b
+
+    def get(shape):
+        if isinstance(shape, tuple):
+            return tuple(get(y) for y in shape)
+        if isinstance(shape, list):
+            (n,) = struct.unpack("<Q", take(8))
+            _check_equal_lengths("deserialize", n, len(shape))
+            return [get(y) for y in shape]
+        dt, d0, d1, d2, d3, count = struct.unpack("<I4QQ", take(44))
+        if dt not in (0, 2):
+            raise ValueError(f"unsupported af::DType index {dt} in weight blob")
+        npdt = np.float32 if dt == 0 else np.float64
+        if count != d0 * d1 * d2 * d3:
+            raise ValueError("element count does not match dims in weight blob")
+        arr = np.frombuffer(take(count * np.dtype(npdt).itemsize), dtype=np.dtype(npdt).newbyteorder("<")).astype(npdt)
+        arr = arr.reshape((d0, d1, d2, d3), order="F")
+        return ctx.array(arr) if ctx is not None else arr
+
+    out = get(like)
+    if buf.read(1):
+        raise ValueError("trailing bytes in bincode weight blob")
+    return out
 
 
 # ---- Net (net.rs:33-96) ----------------------------------------------------------------------------------------
@@ -215,7 +301,7 @@ def _allreduce_update(comm, net: Net, delta, cumulated):
     ctx = comm.ctx
     if delta is None:
         delta = weights_scale(net.get_weights(), 0.0)
-    loss = ctx.array(np.float32([0.0 if cumulated is None else cumulated]))
+    loss = ctx.array([0.0 if cumulated is None else cumulated])
     leaves = [x for x in weights_leaves(delta) if isinstance(x, CuArray)]
     comm.allreduce_sum(leaves + [loss])
     return delta, float(loss.numpy().reshape(-1)[0])
@@ -286,7 +372,7 @@ class WeightData(Net):
         return value, value.gid() if _has_id(value) else ()
 
     def get_weights(self):
-        return self.data.clone() if isinstance(self.data, CuArray) else np.array(self.data, copy=True)
+        return self.data.clone()  # net.rs:357-359 (an O(1) handle copy; `+=` on the net's own handle is copy-on-write)
 
     def set_weights(self, weights) -> None:
         _check_equal_dimensions("set_weights", dims_of(weights), dims_of(self.data))

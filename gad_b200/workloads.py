@@ -93,7 +93,7 @@ def mlp_step(ctx: Context, X: CuArray, Ws: Sequence[CuArray], bs: Sequence[CuArr
     return lossd, gW, gb
 
 
-def mlp_hvp(ctx: Context, X: CuArray, Ws, bs, target: CuArray, vs: Sequence[CuArray], comm: Optional[Comm] = None):
+def mlp_hvp(ctx: Context, X: CuArray, Ws, bs, target: CuArray, vs: Sequence[CuArray], comm: Optional[Comm] = None, overlap: bool = True):
     """C5: Hessian-vector product of the MLP loss by reverse-over-reverse on GraphN:
     g = grad L; s = sum_l dot(g_{W_l}, v_l); hv = grad s. The loss is a sum over batch rows, so with `comm` each rank
     differentiates its rows twice and the products (and the loss) are summed over the ranks."""
@@ -103,8 +103,11 @@ def mlp_hvp(ctx: Context, X: CuArray, Ws, bs, target: CuArray, vs: Sequence[CuAr
     first = g.compute_gradients(loss.gid(), one)
     terms = [g.dot(first.get(w.gid()), g.constant(v)) for w, v in zip(vW, vs)]
     s = g.add_all(terms)
-    second = g.compute_gradients(s.gid(), one)
+    dp = comm is not None and comm.nranks > 1
+    # the second sweep's outputs are what is summed over the ranks: each product travels as soon as the sweep has completed
+    # it, while the layers below are still being differentiated (gadcu_compute_gradients_dp)
+    second = g.compute_gradients(s.gid(), one, comm if dp and overlap else None)
     hv, lossd = [second.get(w.gid()).data() for w in vW], loss.data()
-    if comm is not None and comm.nranks > 1:
-        comm.allreduce_sum(hv + [lossd])
+    if dp:
+        comm.allreduce_sum(([] if overlap else hv) + [lossd])
     return hv, lossd, g.num_nodes()

@@ -13,7 +13,7 @@
  *    launches nothing. gadcu_last_error() returns a thread-local description (variant + dims).
  *  - Arrays are immutable, refcounted, column-major, Dim4-shaped (dim 0 fastest; af::Dim4
  *    convention, gad/src/core.rs:120-136) device buffers of f32 or f64. Every op returns a new
- *    handle (+1 reference owned by the caller). Clone = gadcu_array_retain, O(1).
+ *    handle (+1 reference owned by the caller). Clone = gadcu_array_clone, O(1) (a new handle on the same buffer).
  *  - Scalars produced by array ops (`dot`, `as_scalar`, gad/src/array.rs:106-126) stay on the
  *    device as 1-element "scalar" arrays; gadcu_scalar_to_host reads (and synchronises) on demand.
  *  - A gadcu_value is gad's `Value<D>` (gad/src/graph.rs:35-43): data + optional node id
@@ -127,6 +127,10 @@ GADCU_API gadcu_status gadcu_array_upload(gadcu_array* a, const void* pinned_hos
  * must be issued after gadcu_ctx_wait_uploads(), which makes the compute stream wait for the copies (no host sync). */
 GADCU_API gadcu_status gadcu_array_upload_async(gadcu_array* a, const void* pinned_host);
 GADCU_API gadcu_status gadcu_ctx_wait_uploads(gadcu_ctx* ctx);
+/* af::Array::clone: a NEW handle on the same device buffer, O(1) (what gad's pervasive `.clone()` costs: graph.rs:152-155,
+ * net.rs:100-130 get_weights). Handles made this way are independent values: gadcu_array_add_assign on one of them
+ * leaves the others' contents alone (copy-on-write). gadcu_array_retain, by contrast, adds a reference to the SAME handle. */
+GADCU_API gadcu_status gadcu_array_clone(const gadcu_array* a, gadcu_array** out);
 GADCU_API gadcu_status gadcu_array_retain(gadcu_array* a);
 GADCU_API gadcu_status gadcu_array_release(gadcu_array* a);
 GADCU_API gadcu_status gadcu_array_dims(const gadcu_array* a, gadcu_dim4* out);
@@ -139,7 +143,10 @@ GADCU_API gadcu_status gadcu_value_release(gadcu_value* v);
 /* seeded synthetic data generated on the device (bench / tests): U[lo,hi) or N(mean, std) */
 GADCU_API gadcu_status gadcu_array_random(gadcu_ctx* ctx, gadcu_dtype dt, const gadcu_dim4* dims, uint64_t seed,
                                           int normal, double a, double b, gadcu_array** out);
-/* WeightOps (gad/src/net.rs:161-180): in-place `self += other`, and `self * lambda`. */
+/* WeightOps (gad/src/net.rs:161-180): `self += other`, and `self * lambda`. `+=` follows af::Array's copy-on-write:
+ * the sum is written in place when `self` is the only holder of its buffer; otherwise it goes to a fresh buffer and
+ * `self` is rebound to it, so clones (gadcu_array_clone), weight snapshots and values captured by a tape keep the old
+ * contents. */
 GADCU_API gadcu_status gadcu_array_add_assign(gadcu_array* self, const gadcu_array* other);
 GADCU_API gadcu_status gadcu_array_scale(const gadcu_array* a, double lambda, gadcu_array** out);
 
@@ -283,6 +290,11 @@ GADCU_API gadcu_status gadcu_evaluate_gradients_dp(gadcu_algebra* g, uint32_t ar
 /* Same, and `also` (e.g. the loss of the step) is summed over the ranks in the same small exchange as the bias gradients. */
 GADCU_API gadcu_status gadcu_evaluate_gradients_dp_with(gadcu_algebra* g, uint32_t arena, uint32_t index, gadcu_array* seed, int once,
                                                         gadcu_comm* comm, gadcu_array* const* also, size_t n_also, gadcu_store** out);
+/* GraphN::compute_gradients (graph.rs:307-318) of one batch shard: the backward pass is recorded on this rank's tape as
+ * usual; each variable's gradient is summed over the ranks as soon as the sweep has completed it (on the communicator's
+ * stream, overlapping the rest of the sweep) and the store returns that sum as a constant. Joined before returning. */
+GADCU_API gadcu_status gadcu_compute_gradients_dp(gadcu_algebra* g, uint32_t arena, uint32_t index, const gadcu_value* seed,
+                                                  gadcu_comm* comm, gadcu_store** out);
 GADCU_API gadcu_status gadcu_comm_destroy(gadcu_comm* comm);
 
 #ifdef __cplusplus

@@ -7,7 +7,7 @@
 //
 //   reference (gad/src)                                   here
 //   --------------------------------------------------   -----------------------------------------------------
-//   af::Array<T>, HasDims::dims   core.rs:41-73,120-136   gadcu::Array<T>::{from_host, host, dims}; copy = O(1) retain
+//   af::Array<T>, HasDims::dims   core.rs:41-73,120-136   gadcu::Array<T>::{from_host, host, dims}; copy = O(1) gadcu_array_clone
 //   Value<D> {data, id}, gid()    graph.rs:35-43,321-342  gadcu::Value<T>::{data, id, gid}
 //   Result<_> / Error variants    error.rs:9-40           gadcu::Error (thrown) with .kind in the reference's order
 //   Check                         lib.rs:519-520          gadcu::Check (static functions on Dim4)
@@ -122,7 +122,8 @@ class Array {
     check(gadcu_array_random(ctx.handle(), dtype_of<T>::value, &d, seed, normal, a, b, &h));
     return adopt(h);
   }
-  Array(const Array& o) : h_(o.h_) { if (h_) gadcu_array_retain(h_); }
+  // af::Array::clone: a new handle on the same buffer — `+=` on one copy leaves the others alone (copy-on-write)
+  Array(const Array& o) { if (o.h_) check(gadcu_array_clone(o.h_, &h_)); }
   Array(Array&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
   Array& operator=(Array o) noexcept { std::swap(h_, o.h_); return *this; }
   ~Array() { if (h_) gadcu_array_release(h_); }

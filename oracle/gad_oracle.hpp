@@ -484,6 +484,12 @@ using GenericGradientMapN = GenericGradientMap<true>;
 // ---------------------------------------------------------------------------------------------
 // Graph — graph.rs.
 // ---------------------------------------------------------------------------------------------
+// see Graph::matmul: false (default) = the reference's matmul VJP as written, quirk included
+inline bool& corrected_matmul_adjoint() {
+  static bool on = false;
+  return on;
+}
+
 template <class E>
 struct Config1 {  // graph.rs:250-256
   using EvalAlgebra = E;
@@ -1012,19 +1018,28 @@ class Graph {
   template <class T> Value<T> norm2(const Value<HostArray<T>>& v) { return dot(v, v); }
 
   // ----- MatrixAlgebra: matrix.rs:141-199
+  // The reference's VJP (matrix.rs:164-176) is `dA = matmul(G, B, p1, p2^T)`, `dB = matmul(A, G, p1^T, p2)`: the true
+  // adjoint only when the differentiated operand is not itself transposed; for a transposed operand it
+  // is a Dimensions error (non-square) or the transposed adjoint (square). That is what this oracle reproduces BY DEFAULT
+  // and what the golden fixtures pin. corrected_matmul_adjoint() switches to the true adjoint for transposed operands
+  // (dA = op2(B) G^T, dB = G^T op1(A)) — NOT the reference's behaviour; it exists so the device library's default mode
+  // (gadcu_ctx_set_strict_reference(ctx, 0), which GraphN needs to differentiate through recorded backward GEMMs: C5)
+  // has something to be checked against on the CPU. Identical wherever the reference formula is valid.
   template <class D>
   Value<D> matmul(const Value<D>& v1, const Value<D>& v2, MatProp p1, MatProp p2) {
     D result = eval_.matmul(v1.data, v2.data, p1, p2);
+    const bool fix1 = p1.transposed && corrected_matmul_adjoint(), fix2 = p2.transposed && corrected_matmul_adjoint();
     return make_node<D>(std::move(result), {v1.input(), v2.input()},
-                        [v1, v2, p1, p2](GA& graph, Store& store, const G<D>& gradient) {
+                        [v1, v2, p1, p2, fix1, fix2](GA& graph, Store& store, const G<D>& gradient) {
+                          const MatProp T{true, false};
                           if (v1.id) {
                             const auto& c2 = graph.link(v2);
-                            auto grad = graph.matmul(gradient, c2, p1, p2.transpose());
+                            auto grad = fix1 ? graph.matmul(c2, gradient, p2, T) : graph.matmul(gradient, c2, p1, p2.transpose());
                             store.template add_gradient<G<D>>(graph, *v1.id, grad);
                           }
                           if (v2.id) {
                             const auto& c1 = graph.link(v1);
-                            auto grad = graph.matmul(c1, gradient, p1.transpose(), p2);
+                            auto grad = fix2 ? graph.matmul(gradient, c1, T, p1) : graph.matmul(c1, gradient, p1.transpose(), p2);
                             store.template add_gradient<G<D>>(graph, *v2.id, grad);
                           }
                         });

@@ -355,6 +355,14 @@ int oracle_gradients(void* alg, uint32_t arena, uint32_t index, void* seed, int 
 
 void oracle_store_free(void* p) { delete static_cast<OStore*>(p); }
 
+// 0 (default): the reference's matmul VJP as written (matrix.rs:164-176, quirk for transposed operands included);
+// 1: the true adjoint for transposed operands — the device library's default mode. Returns the previous setting.
+int oracle_set_corrected_adjoint(int on) {
+  const int before = corrected_matmul_adjoint() ? 1 : 0;
+  corrected_matmul_adjoint() = on != 0;
+  return before;
+}
+
 // Returns NULL when the id has no gradient in the store (absent ≠ zero: tests/compare.rs:90-91).
 void* oracle_store_get(void* store, uint32_t arena, uint32_t index, int dtype, int is_scalar) {
   auto* st = static_cast<OStore*>(store);

@@ -60,6 +60,7 @@ extern "C" {
     // arrays: af::Array::new / host / dims / clone / drop
     pub fn gadcu_array_from_host(ctx: *mut gadcu_ctx, dt: c_int, dims: D, host: *const c_void, out: *mut *mut gadcu_array) -> gadcu_status;
     pub fn gadcu_array_to_host(a: *const gadcu_array, host: *mut c_void) -> gadcu_status;
+    pub fn gadcu_array_clone(a: *const gadcu_array, out: *mut *mut gadcu_array) -> gadcu_status;
     pub fn gadcu_array_retain(a: *mut gadcu_array) -> gadcu_status;
     pub fn gadcu_array_release(a: *mut gadcu_array) -> gadcu_status;
     pub fn gadcu_array_dims(a: *const gadcu_array, out: *mut gadcu_dim4) -> gadcu_status;
@@ -198,4 +199,5 @@ extern "C" {
                                        out: *mut *mut gadcu_store) -> gadcu_status;
     pub fn gadcu_evaluate_gradients_dp_with(g: A, arena: u32, index: u32, seed: *mut gadcu_array, once: c_int, comm: *mut gadcu_comm,
                                             also: *const *mut gadcu_array, n_also: usize, out: *mut *mut gadcu_store) -> gadcu_status;
+    pub fn gadcu_compute_gradients_dp(g: A, arena: u32, index: u32, seed: V, comm: *mut gadcu_comm, out: *mut *mut gadcu_store) -> gadcu_status;
 }

@@ -94,9 +94,12 @@ pub struct CuArray<T: CuFloat> {
 unsafe impl<T: CuFloat> Send for CuArray<T> {}
 unsafe impl<T: CuFloat> Sync for CuArray<T> {}
 impl<T: CuFloat> Clone for CuArray<T> {
+    /// af::Array::clone: a NEW handle on the same buffer, so that `+=` on one clone (WeightOps::add_assign,
+    /// net.rs:171-175, copy-on-write in the backend) leaves the others alone — get_weights() snapshots stay snapshots.
     fn clone(&self) -> Self {
-        unsafe { gadcu_array_retain(self.h); }
-        CuArray { h: self.h, _t: PhantomData }
+        let mut h = std::ptr::null_mut();
+        assert_eq!(unsafe { gadcu_array_clone(self.h, &mut h) }, GADCU_OK);
+        CuArray { h, _t: PhantomData }
     }
 }
 impl<T: CuFloat> Drop for CuArray<T> {

@@ -71,8 +71,36 @@ def lib() -> C.CDLL:
         L.oracle_mlp_step.restype = C.c_double
         L.oracle_mlp_step.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
+        L.oracle_set_corrected_adjoint.restype = C.c_int
+        L.oracle_set_corrected_adjoint.argtypes = [C.c_int]
+        L.oracle_set_blas.restype = C.c_int
+        L.oracle_set_blas.argtypes = [C.c_char_p, C.c_int]
+        L.oracle_mlp_hvp_corrected.restype = C.c_double
+        L.oracle_mlp_hvp_corrected.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                               C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p), C.c_int,
+                                               C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
+
+
+def set_corrected_adjoint(on: bool) -> bool:
+    """False (default): the reference's matmul VJP as written (matrix.rs:164-176), quirk for transposed operands
+    included. True: the true adjoint there — the device library's default mode. Returns the previous setting."""
+    return bool(lib().oracle_set_corrected_adjoint(int(on)))
+
+
+def find_blas():
+    """Path of a CBLAS this host has (the OpenBLAS numpy bundles), or None."""
+    import glob
+    d = os.path.join(os.path.dirname(os.path.dirname(np.__file__)), "numpy.libs")
+    hits = sorted(glob.glob(os.path.join(d, "libscipy_openblas*.so*"))) + sorted(glob.glob(os.path.join(d, "libopenblas*.so*")))
+    return hits[0] if hits else None
+
+
+def set_blas(path, threads: int = 0) -> bool:
+    """CPU BASELINE only: the oracle's matmul through a BLAS sgemm, as ArrayFire's CPU backend does it (never used by
+    parity checks: summation order differs from the documented loop). path=None switches back."""
+    return bool(lib().oracle_set_blas(path.encode() if path else None, int(threads)))
 
 
 class OracleError(Exception):
@@ -342,3 +370,20 @@ def mlp_step(X, Ws, bs, target, nthreads: int = 1):
     secs = lib().oracle_mlp_step(B, D, L, Xf.ctypes.data_as(C.c_void_p), ptrs(Wf), ptrs(bf), Tf.ctypes.data_as(C.c_void_p),
                                  loss.ctypes.data_as(C.c_void_p), ptrs(gW), ptrs(gb), nthreads)
     return float(loss[0]), [g.reshape((D, D), order="F") for g in gW], [g.reshape((1, D), order="F") for g in gb], secs
+
+
+def mlp_hvp(X, Ws, bs, target, Vs, nthreads: int = 1):
+    """C5 on the oracle's GraphN with the CORRECTED matmul adjoint (the reference's own VJP cannot differentiate
+    through its backward GEMMs for B != D: SURVEY App. C.2). Returns (loss, [H v]_l, seconds, tape nodes)."""
+    B, D = X.shape
+    L = len(Ws)
+    f = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1, order="F"))
+    Xf, Tf = f(X), f(target)
+    Wf, bf, Vf = [f(w) for w in Ws], [f(b) for b in bs], [f(v) for v in Vs]
+    hv = [np.empty(D * D, dtype=np.float32) for _ in range(L)]
+    loss = np.zeros(1, dtype=np.float32)
+    nodes = C.c_uint64()
+    ptrs = lambda arrs: (C.c_void_p * L)(*[a.ctypes.data_as(C.c_void_p).value for a in arrs])
+    secs = lib().oracle_mlp_hvp_corrected(B, D, L, Xf.ctypes.data_as(C.c_void_p), ptrs(Wf), ptrs(bf), Tf.ctypes.data_as(C.c_void_p),
+                                          ptrs(Vf), loss.ctypes.data_as(C.c_void_p), ptrs(hv), nthreads, C.byref(nodes))
+    return float(loss[0]), [h.reshape((D, D), order="F") for h in hv], secs, int(nodes.value)

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import gad_b200 as gb
+import host_weights as hw
 from gad_b200 import net as gn
 from helpers import to_np
 
@@ -29,7 +30,7 @@ class TestNet(gn.Net):
         return out, (w.gid() if not isinstance(w, tuple) and w.id() is not None else ())
 
     def get_weights(self):
-        return self.weights.clone() if isinstance(self.weights, gb.CuArray) else np.array(self.weights)
+        return self.weights.clone()
 
     def update_weights(self, delta):
         self.weights = gn.weights_add_assign(self.weights, delta)
@@ -104,15 +105,19 @@ def test_training_trajectory_matches_the_oracle(ctx, oracle):
     w0 = rng.standard_normal((3, 3)).astype(np.float32)
     B = rng.standard_normal((3, 3)).astype(np.float32)
     dev = make_net(ctx.array(w0)).add_square_loss()
-    cpu = make_net(w0.copy()).add_square_loss()
+    cpu = make_net(hw.HostWeight(w0)).add_square_loss()
     dev_batch = [(ctx.array(A), ctx.array(I3)), (ctx.array(B), ctx.array(np.float32(0.5) * B))]
     cpu_batch = [(A, I3), (B, np.float32(0.5) * B)]
     for _ in range(25):
         ld = dev.apply_gradient_step(-0.01, dev_batch, lambda: gb.Graph1(ctx))
-        lc = cpu.apply_gradient_step(-0.01, cpu_batch, lambda: oracle.OGraph1())
+        lc = cpu.apply_gradient_step(-0.01, cpu_batch, lambda: hw.OGraph1())
         assert abs(ld - lc) <= 1e-5 * max(1.0, abs(lc))
     wd = dev.get_weights()[1].numpy()[:, :, 0, 0]
     wc = np.asarray(cpu.get_weights()[1]).reshape(3, 3)
+    # the reference's checkpoint layout (bincode + afserde) round-trips through the device
+    blob = gn.serialize_weights_bincode(dev.get_weights())
+    back = gn.deserialize_weights_bincode(blob, like=dev.get_weights(), ctx=ctx)
+    assert np.array_equal(back[1].numpy(), dev.get_weights()[1].numpy())
     assert np.max(np.abs(wd - wc)) <= 1e-5
 
 
