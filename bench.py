@@ -458,7 +458,10 @@ def cpu_baseline_and_parity(ctx, wl, X, T, Ws, bs, device_out):
         dloss, dgW, dgb = wl.mlp_step(ctx, ctx.array(data[0]), Ws, bs, ctx.array(data[3]))
     per_array = {f"dW{l + 1}": rel_err(dgW[l].numpy()[:, :, 0, 0], ogW[l]) for l in range(L)}
     per_array.update({f"db{l + 1}": rel_err(dgb[l].numpy()[:, :, 0, 0], ogb[l]) for l in range(L)})
-    parity = {"max_rel": max(per_array.values()), "vs": "oracle", "per_array": per_array, "loss_rel": abs(dloss.item() - oloss) / abs(oloss),
+    parity = {"max_rel": max(per_array.values()), "vs": "oracle", "per_array": per_array,
+              "loss": {"device": dloss.item(), "oracle": oloss,
+                       "note": "the oracle adds the 33.5 M squared residuals one after the other in f32 (its documented order), which loses whole terms once the "
+                               "running sum passes 2^24; the device's tree sum is the one that agrees with f64 (tests/test_gpu_parity_full.py: 2e-5)"},
               "rows": rows, "what": "max |device - oracle| / max |oracle| over every dL/dW_l and dL/db_l of one step on the same inputs; both are f32 "
               "computations with different summation orders (3xTF32 tensor-core tiles vs a CPU sgemm), so this is f32 rounding of sums over "
               f"{rows} rows, not a bit comparison"}
@@ -546,10 +549,10 @@ def batched_metric(ctx, torch, gb, wl, pk, world, rank, dist):
             compiled = {"error": repr(e)}
         if compiled and "ms_per_call" in compiled:
             grads = res["r"][2]
-            bits = np.uint64(0)
+            bits = 0
             for c in grads:
-                bits = bits + c.numpy()[:4096, 0, 0, 0].view(np.uint64).sum(dtype=np.uint64)
-            compiled["same_bits_as_python_recorded"] = bool(int(bits) == int(compiled.pop("bits_checksum_first_4096_lanes")))
+                bits = (bits + int(c.numpy()[:4096, 0, 0, 0].view(np.uint64).sum(dtype=np.uint64))) % (1 << 64)
+            compiled["same_bits_as_python_recorded"] = bool(bits == int(compiled.pop("bits_checksum_first_4096_lanes")))
             c_ms = compiled["ms_per_call"]
             if dist is not None:
                 t = torch.tensor([c_ms], device="cuda", dtype=torch.float64)
@@ -815,8 +818,8 @@ def hvp_cpu_baseline_and_parity(ctx, wl, X, T, Ws, bs, vs):
     scale = B_TOTAL // rows
     cpu = {"value": 1.0 / (secs * scale), "unit": "HVPs/s", "cores": threads, "kind": "port", "seconds": secs, "gemm": gemm,
            "sample": f"{rows} of {B_TOTAL} batch rows at full width, the device's own inputs; scaled by {scale}x; oracle GraphN with the corrected matmul adjoint"}
-    parity = {"max_rel": max(per.values()), "vs": "oracle (corrected adjoint)", "per_array": per, "loss_rel": abs(dloss.item() - oloss) / abs(oloss),
-              "rows": rows, "tape_nodes_equal": bool(int(dnodes) == int(nodes))}
+    parity = {"max_rel": max(per.values()), "vs": "oracle (corrected adjoint)", "per_array": per, "rows": rows,
+              "tape_nodes_equal": bool(int(dnodes) == int(nodes))}
     return cpu, parity
 
 

