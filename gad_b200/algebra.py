@@ -143,6 +143,10 @@ class Context:
         """Deferred elementwise regions (gadcu_ctx_set_lazy): on by default for arrays of >= 32768 elements."""
         _check(self.lib.gadcu_ctx_set_lazy(self.handle, int(enable), int(min_elements)))
 
+    def set_gemm_epilogue(self, enable: bool) -> None:
+        """Fused GEMM epilogues (gadcu_ctx_set_gemm_epilogue): on by default; off = every product launched where it is recorded."""
+        _check(self.lib.gadcu_ctx_set_gemm_epilogue(self.handle, int(enable)))
+
     def set_strict_reference(self, strict: bool) -> None:
         """True: reproduce the reference's matmul VJP for transposed operands as is."""
         _check(self.lib.gadcu_ctx_set_strict_reference(self.handle, int(strict)))

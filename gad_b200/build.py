@@ -26,9 +26,9 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "-I", os.path.join(ROOT, "include"), "-I", CSRC, "--expt-relaxed-constexpr", "-Xcudafe", "--diag_suppress=177"]
-NO_FMA = {"ew.cu", "reduce.cu", "batched.cu"}
+NO_FMA = {"ew.cu", "reduce.cu", "batched.cu", "gemm_tc.cu"}  # gemm_tc.cu: its fused elementwise epilogues must round like the tape's separate kernels
 SOURCES = ["runtime.cu", "eval.cu", "graph.cu", "capi.cu", "ew.cu", "reduce.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_dmma.cu",
-           "batched.cu", "comm.cu", "jit.cu"]
+           "batched.cu", "comm.cu", "jit.cu", "symm.cu"]
 
 
 def _headers_mtime() -> float:

@@ -204,7 +204,9 @@ class EvalAlgebra final : public Algebra {
   // One kernel: out = [acc +] op(ins...). In place when `acc` is uniquely owned.
   ArrayRef fused(k::EwOp op, ArrayRef acc, std::initializer_list<const ArrayRef*> ins, double c = 0.0, double c2 = 0.0);
   // One GEMM: out = [acc +] op(a)*op(b)
-  ArrayRef matmul_acc(ArrayRef acc, const ArrayRef& a, const ArrayRef& b, MatProp p1, MatProp p2);
+  // `defer`: the product may be recorded as a leaf of a deferred region instead of launched (never for a variable's
+  // gradient, which the caller wants computed where the sweep reaches it)
+  ArrayRef matmul_acc(ArrayRef acc, const ArrayRef& a, const ArrayRef& b, MatProp p1, MatProp p2, bool defer = false);
   // sum_as with the accumulation folded into the last reduction pass
   ArrayRef sum_as_acc(ArrayRef acc, const ArrayRef& v, const Dim4& d);
 

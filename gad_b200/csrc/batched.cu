@@ -32,6 +32,7 @@
 #include <sstream>
 #include <tuple>
 #include <unordered_map>
+#include <unordered_set>
 
 #include "batched.h"
 #include "jit.h"
@@ -44,7 +45,11 @@ enum SymOp : uint16_t {
   S_SIN, S_COS, S_TANH, S_SIGMOID, S_RECIP, S_SQRT, S_SELECT, S_SELECT_R0, S_SELECT_R1, S_MIN, S_MAX, S_STORE,
   // array semantics where they differ from the scalar `impl ... for Eval` (ew.cu functors): 0 - v (arith.rs:60-62),
   // af::log1p, af::minof / af::maxof; tiled loads (a row or a column broadcast over the other dimension)
-  S_NEG0, S_LOG1PF, S_FMIN, S_FMAX, S_LOADCOL, S_LOADROW
+  S_NEG0, S_LOG1PF, S_FMIN, S_FMAX, S_LOADCOL, S_LOADROW,
+  // array mode: the result of a matmul that has been recorded but not launched (SymProgram::pending). A leaf like a load;
+  // by the time a kernel is generated it has a column (the plain GEMM ran) or nothing needs it (the GEMM ran with the
+  // elementwise ops behind it fused into its epilogue and THEIR result has the column).
+  S_GEMM
 };
 
 struct SymInstr {
@@ -88,6 +93,18 @@ struct SymProgram {
   std::map<std::vector<int32_t>, Compiled> compiled;
   std::vector<ArrayRef> launch_compiled(const Compiled& c, size_t nout);
   std::map<std::tuple<uint16_t, int32_t, int32_t, int32_t, int32_t, double>, int32_t> value_number;  // array mode: CSE
+  // array mode: deferred products (register of the S_GEMM instruction -> what to launch). The operands are held.
+  struct PendingGemm {
+    ArrayRef a, b;
+    MatProp p1, p2;
+    Dim4 rd;
+  };
+  std::unordered_map<int32_t, PendingGemm> pending;
+  // columns that must outlive their handles: what a deferred product left behind (its own result, or the result of the
+  // tail fused into it). "Recompute from the operands when the column is gone" would mean launching the GEMM again.
+  std::unordered_set<int32_t> pinned;
+  void resolve_pending(const std::vector<int32_t>& todo);
+  ArrayRef launch_pending(const PendingGemm& pg, const k::GemmEpilogue* epi, bool with_split);
   uint64_t last_instructions = 0, last_slots = 0;
   bool retired = false;      // one of its leaf buffers has been overwritten in place: closed for new instructions (lazy_before_write)
   std::mutex mu;
@@ -125,7 +142,7 @@ struct SymRef {
   ~SymRef() {
     ArrayRef drop;  // released after the lock
     std::lock_guard<std::mutex> lk(prog->mu);
-    if (--prog->live[reg] == 0 && prog->array_mode) {
+    if (--prog->live[reg] == 0 && prog->array_mode && !prog->pinned.count(reg)) {
       // nobody can ask for this register any more: its column (if it was computed) goes back to the pool now;
       // a later value that depends on it recomputes it from its operands
       auto it = prog->cache.find(reg);
@@ -290,6 +307,20 @@ std::vector<ArrayRef> SymProgram::run(const std::vector<int32_t>& outs) {
   if (todo.empty()) return result;
   std::sort(todo.begin(), todo.end());
   todo.erase(std::unique(todo.begin(), todo.end()), todo.end());
+  if (array_mode && !pending.empty()) {
+    // deferred products the request depends on are launched now — with the request's own elementwise chain in the
+    // epilogue where it is one of the known tails — and whatever that settled drops out of the request
+    resolve_pending(todo);
+    std::vector<int32_t> left;
+    for (int32_t r : todo)
+      if (!cache.count(r)) left.push_back(r);
+    todo.swap(left);
+    if (todo.empty()) {
+      for (size_t i = 0; i < outs.size(); i++)
+        if (!result[i]) result[i] = cache[outs[i]];
+      return result;
+    }
+  }
   std::vector<ArrayRef> cols;
   for (size_t first = 0; first < todo.size(); first += kMaxOutputsPerKernel) {
     const std::vector<int32_t> part(todo.begin() + first, todo.begin() + std::min(todo.size(), first + kMaxOutputsPerKernel));
@@ -796,7 +827,7 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
       if (hit) return launch_compiled(compiled[todo], todo.size());
     }
   }
-  auto is_load = [](uint16_t op) { return op == S_LOAD || op == S_LOADU || op == S_LOADCOL || op == S_LOADROW; };
+  auto is_load = [](uint16_t op) { return op == S_LOAD || op == S_LOADU || op == S_LOADCOL || op == S_LOADROW || op == S_GEMM; };
   // 1. what the requested outputs depend on; a register that already has a materialised column is a leaf
   std::vector<char> needed(n, 0);
   std::vector<int32_t> stack(todo.begin(), todo.end());
@@ -1098,6 +1129,179 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   return out_cols;
 }
 
+// ---- deferred products and their fused tails (array mode) ------------------------------------------------------
+ArrayRef SymProgram::launch_pending(const PendingGemm& pg, const k::GemmEpilogue* epi_in, bool with_split) {
+  const ArrayRef &a = pg.a, &b = pg.b;
+  k::GemmArgs g;
+  g.dt = GADCU_F32;
+  g.A = a->ptr();
+  g.B = b->ptr();
+  g.M = pg.rd[0];
+  g.N = pg.rd[1];
+  g.K = pg.p1.transposed ? a->dims[0] : a->dims[1];
+  g.ta = pg.p1.transposed;
+  g.tb = pg.p2.transposed;
+  g.lda = a->dims[0];
+  g.ldb = b->dims[0];
+  g.strideC = g.M * g.N;
+  if (a->ptr() == a->buf->ptr) g.a_buf = a->buf.get();
+  if (b->ptr() == b->buf->ptr) g.b_buf = b->buf.get();
+  ArrayRef out = new_array(ctx, GADCU_F32, pg.rd);
+  g.C = out->ptr();
+  k::GemmEpilogue epi;
+  ArrayRef split;
+  if (epi_in) {
+    epi = *epi_in;
+    if (with_split && g.M % 32 == 0) {
+      // the result is the operand of the next tensor-core products: its [hi | lo] copies are written by the same epilogue
+      // and left on the buffer where split_operand looks for them
+      const uint64_t elems = g.M * g.N;
+      split = new_array(ctx, GADCU_F32, Dim4(2 * elems));
+      epi.hi = static_cast<float*>(split->ptr());
+      epi.lo = epi.hi + elems;
+      Buffer* owner = out->buf.get();
+      owner->split = split->buf.get();
+      owner->split->retain();
+      owner->split_epoch = ctx->epoch.load(std::memory_order_relaxed);
+      owner->split_elems = elems;
+      owner->split_rows = g.M;
+    }
+    g.epi = &epi;
+  }
+  k::launch_gemm(ctx, g);
+  return out;
+}
+
+void SymProgram::resolve_pending(const std::vector<int32_t>& todo) {
+  const int32_t n = int32_t(instrs.size());
+  auto leaf = [&](int32_t r) {
+    const uint16_t op = instrs[r].op;
+    return op == S_LOAD || op == S_LOADU || op == S_LOADCOL || op == S_LOADROW || op == S_CONST || op == S_GEMM || cache.count(r) != 0;
+  };
+  // what the request depends on
+  std::vector<char> needed(n, 0);
+  std::vector<int32_t> stack(todo.begin(), todo.end());
+  while (!stack.empty()) {
+    const int32_t r = stack.back();
+    stack.pop_back();
+    if (needed[r]) continue;
+    needed[r] = 1;
+    if (leaf(r)) continue;
+    const SymInstr& I = instrs[r];
+    for (int32_t x : {I.a, I.b, I.c, I.d})
+      if (x >= 0 && !needed[x]) stack.push_back(x);
+  }
+  std::vector<int32_t> gemms;
+  for (auto& kv : pending)
+    if (needed[kv.first] && !cache.count(kv.first)) gemms.push_back(kv.first);
+  if (gemms.empty()) return;
+  std::sort(gemms.begin(), gemms.end());
+  static const bool fuse_on = [] { const char* e = getenv("GADCU_EPILOGUE"); return !e || atoi(e) != 0; }();
+  static const bool split_on = [] { const char* e = getenv("GADCU_EPILOGUE_SPLIT"); return !e || atoi(e) != 0; }();
+  // a dense [lanes] operand the epilogue can read by pointer: a computed column or a dense load
+  auto dense_ptr = [&](int32_t r) -> const float* {
+    auto c = cache.find(r);
+    if (c != cache.end()) return static_cast<const float*>(c->second->ptr());
+    if (instrs[r].op == S_LOAD) return static_cast<const float*>(inputs[instrs[r].a]->ptr());
+    return nullptr;
+  };
+  // the bias of an add(matmul, tile_as(b, [M, N])): a [1, N] array read as column tile with d0 == M
+  auto bias_ptr = [&](int32_t r, const PendingGemm& pg) -> const float* {
+    const SymInstr& I = instrs[r];
+    if (I.op != S_LOADCOL || cache.count(r)) return nullptr;
+    if (input_d0[I.a] != pg.rd[0] || inputs[I.a]->phys.elements() != pg.rd[1]) return nullptr;
+    return static_cast<const float*>(inputs[I.a]->ptr());
+  };
+  for (int32_t g : gemms) {
+    const PendingGemm& pg = pending.at(g);
+    // every needed instruction that reads g, and what reads those: the product may be fused only if all of that is the
+    // inside of ONE known tail ending in a requested register
+    std::vector<int32_t> readers;
+    for (int32_t r = 0; r < n; r++) {
+      if (!needed[r] || leaf(r)) continue;
+      const SymInstr& I = instrs[r];
+      if (I.a == g || I.b == g || I.c == g || I.d == g) readers.push_back(r);
+    }
+    k::GemmEpilogue epi;
+    int32_t result_reg = -1;
+    std::vector<int32_t> inside;  // registers of the tail other than its result
+    bool split = false;
+    if (fuse_on && readers.size() == 1) {
+      const int32_t r1 = readers[0];
+      const SymInstr& I1 = instrs[r1];
+      auto other = [&](const SymInstr& I) { return I.a == g ? I.b : I.a; };
+      auto sole_reader = [&](int32_t x) {  // the one needed instruction that reads x, or -1
+        int32_t found = -1;
+        for (int32_t r = 0; r < n; r++) {
+          if (!needed[r] || leaf(r)) continue;
+          const SymInstr& I = instrs[r];
+          if (I.a == x || I.b == x || I.c == x || I.d == x) {
+            if (found >= 0) return int32_t(-1);
+            found = r;
+          }
+        }
+        return found;
+      };
+      const bool r1_requested = std::binary_search(todo.begin(), todo.end(), r1);
+      if (I1.op == S_ADD && !r1_requested) {
+        const float* bias = bias_ptr(other(I1), pg);
+        const int32_t r2 = bias ? sole_reader(r1) : -1;
+        if (r2 >= 0 && std::binary_search(todo.begin(), todo.end(), r2)) {
+          const SymInstr& I2 = instrs[r2];
+          if (I2.op == S_TANH && I2.a == r1) {  // tanh(add(matmul, tile_as(b)))
+            epi.kind = k::GemmEpilogue::BIAS_TANH;
+            epi.bias = bias;
+            result_reg = r2;
+            inside = {r1};
+            split = true;
+          } else if (I2.op == S_SUB && I2.b == r1 && I2.a != r1 && dense_ptr(I2.a)) {  // sub(target, add(matmul, tile_as(b)))
+            epi.kind = k::GemmEpilogue::BIAS_RESIDUAL;
+            epi.bias = bias;
+            epi.aux = dense_ptr(I2.a);
+            result_reg = r2;
+            inside = {r1};
+          }
+        }
+      } else if (I1.op == S_MUL && r1_requested && I1.a != I1.b) {
+        // mul(g, addc(neg0(mul(t, t)), 1)): the tanh VJP (analytic.rs:385-395) on an incoming product
+        const int32_t e = other(I1);
+        if (e >= 0 && !leaf(e) && instrs[e].op == S_ADDC && instrs[e].imm == 1.0) {
+          const int32_t ng = instrs[e].a;
+          if (ng >= 0 && !leaf(ng) && instrs[ng].op == S_NEG0) {
+            const int32_t sq = instrs[ng].a;
+            if (sq >= 0 && !leaf(sq) && instrs[sq].op == S_MUL && instrs[sq].a == instrs[sq].b && dense_ptr(instrs[sq].a)) {
+              epi.kind = k::GemmEpilogue::TANH_GRAD;
+              epi.aux = dense_ptr(instrs[sq].a);
+              result_reg = r1;
+              split = true;
+            }
+          }
+        }
+      }
+    }
+    if (result_reg >= 0) {
+      k::GemmArgs probe;  // (shape check only)
+      probe.dt = GADCU_F32;
+      probe.M = pg.rd[0]; probe.N = pg.rd[1];
+      probe.K = pg.p1.transposed ? pg.a->dims[0] : pg.a->dims[1];
+      probe.ta = pg.p1.transposed; probe.tb = pg.p2.transposed;
+      probe.lda = pg.a->dims[0]; probe.ldb = pg.b->dims[0];
+      if (!k::gemm_epilogue_supported(probe)) result_reg = -1;
+    }
+    if (result_reg >= 0) {
+      cache[result_reg] = launch_pending(pg, &epi, split && split_on);
+      pinned.insert(result_reg);
+    } else {
+      cache[g] = launch_pending(pg, nullptr, false);
+      pinned.insert(g);
+    }
+  }
+}
+
+// matmul recorded instead of launched (EvalAlgebra::matmul when deferred regions are on): the product joins the region of
+// its [M, N] result as a leaf, so that the elementwise ops a layer puts behind it can ride in the GEMM's epilogue.
+ArrayRef lazy_matmul(gadcu_ctx* ctx, const ArrayRef& a, const ArrayRef& b, MatProp p1, MatProp p2, const Dim4& rd);
+
 // ---- the symbolic per-lane eval algebra ---------------------------------------------------------
 class SymAlgebra final : public Algebra {
  public:
@@ -1347,6 +1551,23 @@ ArrayRef lazy_elementwise(gadcu_ctx* ctx, k::EwOp op, const ArrayRef& acc, const
   return sym_array(prog, r, dims, is_scalar);
 }
 
+ArrayRef lazy_matmul(gadcu_ctx* ctx, const ArrayRef& a_in, const ArrayRef& b_in, MatProp p1, MatProp p2, const Dim4& rd) {
+  // the program keeps the operands' BUFFERS, through handles of its own: a computed deferred value still carries the
+  // handle of the program that computed it, and holding that here would tie the program to itself for good
+  const ArrayRef a = view_array(a_in, a_in->dims, a_in->phys, a_in->is_scalar), b = view_array(b_in, b_in->dims, b_in->phys, b_in->is_scalar);
+  std::shared_ptr<SymProgram> prog = lazy_program(ctx, GADCU_F32, rd.elements());
+  int32_t r;
+  {
+    std::lock_guard<std::mutex> lk(prog->mu);
+    SymInstr I{uint16_t(S_GEMM)};
+    prog->instrs.push_back(I);  // (never value-numbered: two products are two launches)
+    prog->live.push_back(0);
+    r = int32_t(prog->instrs.size() - 1);
+    prog->pending.emplace(r, SymProgram::PendingGemm{a, b, p1, p2, rd});
+  }
+  return sym_array(prog, r, rd, false);
+}
+
 // Before `buffer` is overwritten in place (WeightOps::add_assign, an upload, an all-reduce): compute every value
 // that still has a handle and would read the old contents later — in EVERY program that can still be asked for
 // values (the open ones and those of earlier tapes that live on through their handles). A program that loads the
@@ -1378,6 +1599,9 @@ void lazy_before_write(gadcu_ctx* ctx, const void* buffer) {
         const SymInstr& I = prog->instrs[r];
         if (I.op == S_LOAD || I.op == S_LOADU || I.op == S_LOADCOL || I.op == S_LOADROW) {
           dep[r] = prog->inputs[I.a]->ptr() == buffer;
+        } else if (I.op == S_GEMM) {
+          auto pg = prog->pending.find(r);  // a product not launched yet reads its operands when it is
+          dep[r] = pg != prog->pending.end() && !prog->cache.count(r) && (pg->second.a->ptr() == buffer || pg->second.b->ptr() == buffer);
         } else if (I.op != S_CONST) {
           // (true data dependence, also THROUGH registers that already have a column: such a column goes back to the
           // pool with its last handle, and a live value above it would then be recomputed from the overwritten leaf)

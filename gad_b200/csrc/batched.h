@@ -17,6 +17,9 @@ std::vector<ArrayRef> batched_rerun(Store& store, const std::vector<ArrayRef>& c
 bool lazy_enabled(gadcu_ctx* ctx, uint64_t n, bool is_scalar);
 ArrayRef lazy_elementwise(gadcu_ctx* ctx, k::EwOp op, const ArrayRef& acc, const std::vector<const ArrayRef*>& ins, double c, double c2,
                           gadcu_dtype dt, const Dim4& dims, bool is_scalar);
+// a matmul recorded as a leaf of the region of its result (launched when something needs it, with the elementwise tail
+// behind it in the GEMM's epilogue where that is one of the known ones: GemmEpilogue)
+ArrayRef lazy_matmul(gadcu_ctx* ctx, const ArrayRef& a, const ArrayRef& b, MatProp p1, MatProp p2, const Dim4& rd);
 void lazy_before_write(gadcu_ctx* ctx, const void* buffer);
 void lazy_flush(const std::vector<ArrayRef>& values);
 

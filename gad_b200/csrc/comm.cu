@@ -15,6 +15,7 @@
 
 #include "algebra.h"
 #include "batched.h"
+#include "symm.h"
 
 namespace {
 
@@ -22,7 +23,7 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclFloat32 = 7, ncclFloat64 = 8 };
-enum { ncclSum = 0 };
+enum { ncclSum = 0, ncclMin = 3 };
 
 struct Nccl {
   void* lib = nullptr;
@@ -65,26 +66,37 @@ void nccl_check(ncclResult_t r, const char* what) {
 
 }  // namespace
 
-// ---- symmetric peer memory for the fused GEMM -> reduce-scatter -> all-gather exchange ---------------------
-// One cudaMalloc per rank, opened by every other rank through CUDA IPC (handles travel through an NCCL all-gather):
-//   [ flags: 2 x 32 x u32 | small: 2 x 8 x kSmallBytes | staging: kSlots x slot_bytes | result: kSlots x slot_bytes ]
-// staging[slot] receives, for every tile this rank owns, the nranks partial tiles (pushed by the GEMM epilogues of all
-// ranks); result[slot] receives the reduced gradient in its final column-major layout (pushed by every owner);
+// ---- symmetric memory for the gradient exchange --------------------------------------------------------------------
+// One region per rank (symm.cu), mapped into every process and, where the fabric has it, bound to a multicast object:
+//   [ flags: 3 sets | small: 2 x 8 x kSmallBytes | data ]
+// flag sets 0 / 1: cross-rank barriers issued on the communicator's / the compute stream (32 words each); set 2: the
+// per-block barriers of the NVLS exchange kernel (kNvlsMaxBlocks x 8 words).
 // small[parity][r] receives rank r's copy of a batch of small arrays (biases, the loss) to be summed locally.
-// Barriers issued on the communicator's stream and on the compute stream count separately (flag set 0 / 1).
+// data, NVLS mode   : kSlotsNv gradient-sized slots. A dW GEMM writes its partial product straight into a slot; one kernel
+//                     then sums every element over the ranks INSIDE the switch (multimem.ld_reduce) and stores the sum to
+//                     all ranks (multimem.st), each rank doing 1/N of the elements; the slot IS the gradient array the
+//                     store hands out (no staging, no copy-out).
+// data, legacy mode : staging[kSlots] (partial tiles pushed by every rank's GEMM epilogue) + result[kSlots], as in round 1.
 constexpr int kSlots = 3;
+constexpr int kSlotsNv = 6;  // two steps' worth of weight gradients: a step's results may be held while the next one runs
+constexpr int kNvlsMaxBlocks = 128;
 constexpr size_t kSmallBytes = 256 * 1024;
-constexpr size_t kHeapHeader = 256 + 2 * 8 * kSmallBytes;
+constexpr size_t kFlagBytes = 2 * 32 * 4 + size_t(kNvlsMaxBlocks) * 8 * 4;  // 4352
+constexpr size_t kHeapHeader = 8192 + 2 * 8 * kSmallBytes;
 struct SymmHeap {
-  size_t slot_bytes = 0;
+  size_t slot_bytes = 0;   // legacy: 2 x gradient bytes (k-split pushes two partial blocks); NVLS: capacity of one slot
+  size_t grad_bytes = 0;   // the gradient size the heap was made for
   void* local = nullptr;
   void* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // peer[rank] == local
-  uint32_t* flags(int r, int set) const { return static_cast<uint32_t*>(peer[r]) + 32 * set; }
+  void* mc = nullptr;      // multicast mapping of the whole region (NVLS), or null
+  gadcu::SymmRegion region;
+  uint32_t* flags(int r, int set) const { return static_cast<uint32_t*>(peer[r]) + (set < 2 ? 32 * set : 64); }
   float* small(int r, int parity, int src) const {
-    return reinterpret_cast<float*>(static_cast<char*>(peer[r]) + 256 + (size_t(parity) * 8 + size_t(src)) * kSmallBytes);
+    return reinterpret_cast<float*>(static_cast<char*>(peer[r]) + 8192 + (size_t(parity) * 8 + size_t(src)) * kSmallBytes);
   }
   float* staging(int r, int slot) const { return reinterpret_cast<float*>(static_cast<char*>(peer[r]) + kHeapHeader + size_t(slot) * slot_bytes); }
   float* result(int r, int slot) const { return reinterpret_cast<float*>(static_cast<char*>(peer[r]) + kHeapHeader + size_t(kSlots + slot) * slot_bytes); }
+  size_t nv_offset(int slot) const { return kHeapHeader + size_t(slot) * grad_bytes; }  // byte offset of NVLS slot `slot` in every mapping
 };
 
 struct gadcu_comm {
@@ -102,6 +114,15 @@ struct gadcu_comm {
   std::vector<std::pair<const gadcu_array*, gadcu::ArrayRef>> replaced;  // this sweep: gradient array -> the private copy reduced in its place
   bool no_peer_memory = false;    // CUDA IPC / peer access unavailable: everything goes through NCCL
   std::vector<std::pair<const char*, cudaEvent_t>> trace;  // GADCU_DP_TRACE=1: timeline of one step
+  // NVLS exchange
+  bool nvls = false;              // the heap has a multicast mapping and GADCU_DP_NVLS != 0
+  uint64_t nv_exchanges = 0;      // slot = nv_exchanges % kSlotsNv
+  uint32_t nv_seq = 0;            // barrier sequence numbers of the exchange kernel (two per launch)
+  gadcu::Ref<gadcu::Buffer> nv_slot_buf[kSlotsNv];  // the gradient array living in each slot (copied out if still held when the slot comes round)
+  cudaEvent_t nv_slot_done[kSlotsNv] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::string key;                // rendezvous key of this communicator (hash of the NCCL id)
+  std::string heap_kind;          // how the symmetric memory was obtained (symm.cu)
+  uint64_t heaps_made = 0;
 };
 
 using namespace gadcu;
@@ -127,6 +148,11 @@ gadcu_status gadcu_comm_init(gadcu_ctx* ctx, int nranks, int rank, const void* i
       ncclUniqueId id;
       std::memcpy(&id, id_128_bytes, sizeof(id));
       nccl_check(nccl().CommInitRank(&c->comm, nranks, id, rank), "ncclCommInitRank");
+      uint64_t h = 1469598103934665603ull;
+      for (unsigned char b : id.internal) { h ^= b; h *= 1099511628211ull; }
+      char hex[32];
+      snprintf(hex, sizeof(hex), "%016llx", (unsigned long long)h);
+      c->key = hex;
       int lo = 0, hi = 0;
       GADCU_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       GADCU_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));  // collectives first when SMs free up
@@ -223,37 +249,178 @@ __global__ void __launch_bounds__(256) dp_scatter_kernel(const float* __restrict
   }
 }
 
+// host-side collectives for the rendezvous of symm.cu, on top of NCCL (device scratch, context stream, synchronous)
+gadcu::SymmCollectives nccl_collectives(gadcu_comm* comm) {
+  gadcu::SymmCollectives c;
+  c.allreduce_min = [comm](int v) {
+    gadcu_ctx* ctx = comm->ctx;
+    int* dev = nullptr;
+    GADCU_CUDA(cudaMalloc(&dev, sizeof(int)));
+    GADCU_CUDA(cudaMemcpyAsync(dev, &v, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    nccl_check(nccl().AllReduce(dev, dev, 1, /*ncclInt32*/ 2, ncclMin, comm->comm, ctx->stream), "ncclAllReduce(min)");
+    int out = 0;
+    GADCU_CUDA(cudaMemcpyAsync(&out, dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GADCU_CUDA(cudaStreamSynchronize(ctx->stream));
+    GADCU_CUDA(cudaFree(dev));
+    return out;
+  };
+  c.allgather = [comm](const void* mine, void* all, size_t bytes) {
+    gadcu_ctx* ctx = comm->ctx;
+    if (!nccl().AllGather) fail(GADCU_ERR_NCCL, "ncclAllGather is not available");
+    char* dev = nullptr;
+    GADCU_CUDA(cudaMalloc(&dev, bytes * size_t(comm->nranks + 1)));
+    GADCU_CUDA(cudaMemcpyAsync(dev, mine, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    nccl_check(nccl().AllGather(dev, dev + bytes, bytes, /*ncclUint8*/ 1, comm->comm, ctx->stream), "ncclAllGather");
+    GADCU_CUDA(cudaMemcpyAsync(all, dev + bytes, bytes * size_t(comm->nranks), cudaMemcpyDeviceToHost, ctx->stream));
+    GADCU_CUDA(cudaStreamSynchronize(ctx->stream));
+    GADCU_CUDA(cudaFree(dev));
+  };
+  return c;
+}
+
+void nvls_selfbench(gadcu_comm* comm);
+// Every rank calls this at the same point of the same step, with the same `bytes` (the size of the gradient coming through).
 void ensure_heap(gadcu_comm* comm, size_t bytes) {
-  if (comm->heap.slot_bytes >= bytes) return;
+  if (comm->heap.grad_bytes >= bytes) return;
   if (comm->heap.local) {  // sized by the first gradient that came through; a larger one later goes through NCCL
     throw GadError(GADCU_ERR_UNSUPPORTED, "gradient larger than the symmetric heap");
   }
   if (comm->nranks > 8) fail(GADCU_ERR_UNSUPPORTED, "data-parallel exchange: at most 8 ranks");
   gadcu_ctx* ctx = comm->ctx;
-  Nccl& nc = nccl();
-  if (!nc.AllGather) fail(GADCU_ERR_NCCL, "ncclAllGather is not available");
   SymmHeap& h = comm->heap;
-  h.slot_bytes = (bytes + 255) / 256 * 256;
-  const size_t total = kHeapHeader + size_t(2 * kSlots) * h.slot_bytes;
-  GADCU_CUDA(cudaMalloc(&h.local, total));
-  GADCU_CUDA(cudaMemsetAsync(h.local, 0, 256, ctx->stream));
-  // exchange the IPC handles through NCCL (every rank calls this at the same point of the same step)
-  cudaIpcMemHandle_t mine;
-  GADCU_CUDA(cudaIpcGetMemHandle(&mine, h.local));
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  char* dev = nullptr;
-  GADCU_CUDA(cudaMalloc(&dev, 64 * size_t(comm->nranks + 1)));
-  GADCU_CUDA(cudaMemcpyAsync(dev, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
-  nccl_check(nc.AllGather(dev, dev + 64, 64, /*ncclUint8*/ 1, comm->comm, ctx->stream), "ncclAllGather");
-  std::vector<cudaIpcMemHandle_t> all(comm->nranks);
-  GADCU_CUDA(cudaMemcpyAsync(all.data(), dev + 64, 64 * size_t(comm->nranks), cudaMemcpyDeviceToHost, ctx->stream));
+  static const bool want_nvls = [] { const char* e = getenv("GADCU_DP_NVLS"); return !e || atoi(e) != 0; }();
+  const size_t grad = (bytes + 255) / 256 * 256;
+  const size_t legacy_slot = 2 * grad;  // (a k-split GEMM pushes two partial blocks per tile and rank)
+  const size_t data = std::max(size_t(2 * kSlots) * legacy_slot, size_t(kSlotsNv) * grad);
+  const size_t total = kHeapHeader + data;
+  gadcu::symm_alloc(h.region, ctx->device, comm->nranks, comm->rank, total, want_nvls, comm->key + "-" + std::to_string(comm->heaps_made++),
+                    nccl_collectives(comm), &comm->heap_kind);
+  h.local = h.region.local;
+  for (int r = 0; r < comm->nranks; r++) h.peer[r] = h.region.peer[r];
+  h.mc = h.region.mc;
+  h.slot_bytes = legacy_slot;
+  h.grad_bytes = grad;
+  comm->nvls = want_nvls && h.mc != nullptr;
+  // the flags start at zero on every rank before anybody signals
+  GADCU_CUDA(cudaMemsetAsync(h.local, 0, 8192, ctx->stream));
   GADCU_CUDA(cudaStreamSynchronize(ctx->stream));
-  GADCU_CUDA(cudaFree(dev));
-  for (int r = 0; r < comm->nranks; r++) {
-    if (r == comm->rank) { h.peer[r] = h.local; continue; }
-    GADCU_CUDA(cudaIpcOpenMemHandle(&h.peer[r], all[r], cudaIpcMemLazyEnablePeerAccess));
-  }
+  nccl_collectives(comm).allreduce_min(1);
   for (int s = 0; s < kSlots; s++) GADCU_CUDA(cudaEventCreateWithFlags(&comm->slot_done[s], cudaEventDisableTiming));
+  for (int s = 0; s < kSlotsNv; s++) GADCU_CUDA(cudaEventCreateWithFlags(&comm->nv_slot_done[s], cudaEventDisableTiming));
+  if (comm->nvls && getenv("GADCU_NVLS_BENCH")) nvls_selfbench(comm);
+  if (getenv("GADCU_DP_TRACE") && comm->rank == 0)
+    fprintf(stderr, "[dp] symmetric heap: %zu MiB per rank, %s; exchange = %s\n", total >> 20, comm->heap_kind.c_str(),
+            comm->nvls ? "NVLS (multimem.ld_reduce + multimem.st, gradients live in the heap)" : "tile-pushing GEMM epilogue + owner reduce/publish");
+}
+
+// ---- the NVLS exchange kernel -----------------------------------------------------------------------------------
+// One launch per gradient (or per column chunk of the sweep's last one), every rank at once, on the communicator's stream:
+//   1. block b of every rank meets block b of every other rank (flags in peer memory): all partial products are complete
+//      — each rank's GEMM finished before its kernel started (stream order), and the release / acquire pair at system
+//      scope makes those stores visible to the switch's reads;
+//   2. this rank's 1/N share of the float4s: multimem.ld_reduce.add.v4.f32 — the NVSwitch reads the address in all N
+//      memories and returns the sum (the order in which the switch adds the N terms is fixed by the fabric, not by us:
+//      the result is reproducible run to run on one topology and differs from a rank-ordered sum by f32 rounding of an
+//      N-term sum) — then multimem.st.v4.f32: one store, the switch writes all N memories;
+//   3. the blocks meet again: every rank's memory now holds every share.
+// The slot the GEMM wrote its partial product into is overwritten element by element with the sum: it IS the gradient.
+struct NvFlags { uint32_t* p[8]; };
+__device__ __forceinline__ void nv_block_sync(const NvFlags& f, int nranks, int rank, uint32_t seq) {
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < nranks) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[t] + blockIdx.x * 8 + rank), "r"(seq) : "memory");
+    uint32_t seen;
+    unsigned long long t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f.p[rank] + blockIdx.x * 8 + t) : "memory");
+      if (seen >= seq) break;
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > 20000000000ull) __trap();  // a lost rank must not hang the GPU for good
+    } while (true);
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+extern "C++" {
+template <int U>
+__global__ void __launch_bounds__(512) dp_nvls_allreduce_kernel(NvFlags flags, float4* __restrict__ mc, uint64_t v0, uint64_t v1, int nranks, int rank,
+                                                                uint32_t seq) {
+  nv_block_sync(flags, nranks, rank, seq);
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  uint64_t i = v0 + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  // U independent switch reductions in flight per thread (the round trip through the NVSwitch is several microseconds:
+  // bandwidth = bytes in flight / latency)
+  for (; i + (U - 1) * stride < v1; i += U * stride) {
+    float4 a[U];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w)
+                   : "l"(mc + i + u * stride)
+                   : "memory");
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + i + u * stride), "f"(a[u].x), "f"(a[u].y), "f"(a[u].z),
+                   "f"(a[u].w)
+                   : "memory");
+  }
+  for (; i < v1; i += stride) {
+    float4 a;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(mc + i) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + i), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+  }
+  nv_block_sync(flags, nranks, rank, seq + 1);
+}
+}  // extern "C++"
+
+// Sum [byte_offset, byte_offset + bytes) of the heap over the ranks in place (both multiples of 16), on the communicator's stream.
+void nvls_allreduce_cfg(gadcu_comm* comm, size_t byte_offset, size_t bytes, unsigned blocks, int unroll) {
+  const uint64_t base = byte_offset / 16, V = bytes / 16;
+  const uint64_t v0 = base + V * uint64_t(comm->rank) / uint64_t(comm->nranks), v1 = base + V * uint64_t(comm->rank + 1) / uint64_t(comm->nranks);
+  NvFlags f;
+  for (int r = 0; r < 8; r++) f.p[r] = r < comm->nranks ? comm->heap.flags(r, 2) : nullptr;
+  comm->nv_seq += 2;
+  float4* mc = static_cast<float4*>(comm->heap.mc);
+  if (unroll >= 16) dp_nvls_allreduce_kernel<16><<<blocks, 512, 0, comm->stream>>>(f, mc, v0, v1, comm->nranks, comm->rank, comm->nv_seq - 1);
+  else if (unroll >= 8) dp_nvls_allreduce_kernel<8><<<blocks, 512, 0, comm->stream>>>(f, mc, v0, v1, comm->nranks, comm->rank, comm->nv_seq - 1);
+  else dp_nvls_allreduce_kernel<4><<<blocks, 512, 0, comm->stream>>>(f, mc, v0, v1, comm->nranks, comm->rank, comm->nv_seq - 1);
+  comm->ctx->count_launch();
+}
+void nvls_allreduce(gadcu_comm* comm, size_t byte_offset, size_t bytes) {
+  static const unsigned blocks = [] {
+    const char* e = getenv("GADCU_NVLS_BLOCKS");
+    return unsigned(std::max(1, std::min(kNvlsMaxBlocks, e ? atoi(e) : 64)));
+  }();
+  static const int unroll = [] { const char* e = getenv("GADCU_NVLS_UNROLL"); return e ? atoi(e) : 8; }();
+  nvls_allreduce_cfg(comm, byte_offset, bytes, blocks, unroll);
+}
+// GADCU_NVLS_BENCH=1: right after the heap is up, time the exchange kernel alone over one slot for a grid of launch shapes
+void nvls_selfbench(gadcu_comm* comm) {
+  const size_t bytes = comm->heap.grad_bytes;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  GADCU_CUDA(cudaMemsetAsync(static_cast<char*>(comm->heap.local) + comm->heap.nv_offset(0), 0, bytes, comm->stream));
+  for (unsigned blocks : {8u, 16u, 32u, 64u, 128u})
+    for (int unroll : {4, 8, 16}) {
+      for (int w = 0; w < 3; w++) nvls_allreduce_cfg(comm, comm->heap.nv_offset(0), bytes, blocks, unroll);
+      cudaEventRecord(e0, comm->stream);
+      const int reps = 20;
+      for (int i = 0; i < reps; i++) nvls_allreduce_cfg(comm, comm->heap.nv_offset(0), bytes, blocks, unroll);
+      cudaEventRecord(e1, comm->stream);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (comm->rank == 0)
+        fprintf(stderr, "[nvls bench] %d ranks, %zu MiB, blocks %3u x 512 threads, %2d in flight: %.4f ms per all-reduce = %.1f GB/s (bytes / time)\n", comm->nranks,
+                bytes >> 20, blocks, unroll, ms / reps, double(bytes) / (ms / reps * 1e-3) / 1e9);
+    }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
 }
 
 bool tracing() {
@@ -357,6 +524,73 @@ bool small_allreduce(gadcu_comm* comm, gadcu_array* const* arrays, size_t n) {
   return true;
 }
 
+// NVLS form of the exchange: the GEMM is the ordinary one (no pushing epilogue, full speed, last-wave split and all) and
+// writes its partial product into a slot of the symmetric heap; ONE kernel on the communicator's stream sums the slot
+// over the ranks in place, overlapping whatever the sweep does next; the slot is handed out as the gradient array.
+// A slot comes round again kSlotsNv exchanges later: if somebody still holds its array then, the contents move to
+// ordinary memory first (the handle is rebound; holders notice nothing).
+ArrayRef dp_gemm_nvls(gadcu_comm* comm, const k::GemmArgs& g, const Dim4& rd, bool last) {
+  gadcu_ctx* ctx = comm->ctx;
+  const size_t bytes = size_t(g.M) * g.N * 4;
+  const int slot = int(comm->nv_exchanges % kSlotsNv);
+  const bool used_before = comm->nv_exchanges >= uint64_t(kSlotsNv);
+  comm->nv_exchanges++;
+  if (Buffer* old = comm->nv_slot_buf[slot].get()) {
+    if (old->refs.load() > 1) {  // still held by a store / the caller: its data leaves the heap before the slot is written again
+      std::shared_ptr<Pool> pool = ctx->active_pool();
+      void* moved = pool->take(old->bytes);
+      GADCU_CUDA(cudaMemcpyAsync(moved, old->ptr, old->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+      old->ptr = moved;
+      old->pool = pool;
+    }
+    comm->nv_slot_buf[slot].reset();
+  }
+  // peers finished reading / writing this slot for its previous exchange when that exchange's kernel finished here
+  if (used_before) GADCU_CUDA(cudaStreamWaitEvent(ctx->stream, comm->nv_slot_done[slot], 0));
+  auto* buf = new Buffer;
+  buf->ctx = ctx;
+  buf->bytes = bytes;
+  buf->ptr = static_cast<char*>(comm->heap.local) + comm->heap.nv_offset(slot);  // pool == null: the heap owns the memory
+  comm->nv_slot_buf[slot] = Ref<Buffer>(buf, false);
+  auto* arr = new gadcu_array;
+  arr->buf = comm->nv_slot_buf[slot];
+  arr->dims = rd;
+  arr->phys = rd;
+  arr->dtype = GADCU_F32;
+  arr->ctx = ctx;
+  ArrayRef out(arr, false);
+  // the sweep's LAST gradient has nothing left to hide behind: cut into column chunks, the exchange of one chunk overlaps
+  // the GEMM of the next and only the last chunk's exchange is exposed
+  static const uint64_t max_chunks = [] { const char* e = getenv("GADCU_DP_TAIL_CHUNKS"); return e ? uint64_t(std::max(1, atoi(e))) : uint64_t(2); }();
+  uint64_t chunks = 1;
+  if (last && !g.tb)
+    while (chunks * 2 <= max_chunks && g.N % (chunks * 2 * 256) == 0 && (bytes / (chunks * 2)) % (16 * 8) == 0) chunks *= 2;
+  const uint64_t Nc = g.N / chunks;
+  const float* Bfull = static_cast<const float*>(g.B);
+  for (uint64_t c = 0; c < chunks; c++) {
+    k::GemmArgs gc = g;
+    gc.push = nullptr;
+    gc.N = Nc;
+    gc.B = Bfull + c * Nc * g.ldb;
+    if (chunks > 1) gc.b_buf = nullptr;
+    gc.C = static_cast<float*>(out->ptr()) + c * Nc * g.M;
+    mark(comm, "compute: gemm start", ctx->stream);
+    k::launch_gemm(ctx, gc);
+    mark(comm, "compute: gemm end", ctx->stream);
+    cudaEvent_t ev;
+    GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    GADCU_CUDA(cudaEventRecord(ev, ctx->stream));
+    GADCU_CUDA(cudaStreamWaitEvent(comm->stream, ev, 0));
+    GADCU_CUDA(cudaEventDestroy(ev));
+    mark(comm, "comm: after gemm", comm->stream);
+    nvls_allreduce(comm, comm->heap.nv_offset(slot) + size_t(c) * Nc * g.M * 4, size_t(Nc) * g.M * 4);
+    mark(comm, "comm: nvls all-reduce done", comm->stream);
+  }
+  GADCU_CUDA(cudaEventRecord(comm->nv_slot_done[slot], comm->stream));
+  comm->pending++;
+  return out;
+}
+
 // The matmul VJP's product IS a variable's gradient: compute it with the tile-pushing epilogue and run the rest of
 // the exchange on the communicator's stream. Returns the array that holds the rank-summed gradient after the join.
 ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, MatProp p1, MatProp p2, bool last) {
@@ -382,7 +616,7 @@ ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, M
   if (!k::gemm_push_supported(g) || comm->no_peer_memory) return ArrayRef();
   const size_t bytes = size_t(g.M) * g.N * 4;
   try {
-    ensure_heap(comm, 2 * bytes);  // (a k-split GEMM pushes two partial blocks per tile and rank)
+    ensure_heap(comm, bytes);
   } catch (const GadError& e) {
     // no peer memory on this system (IPC disabled, no P2P): decline — the gradient then travels through the grouped
     // NCCL all-reduce at the end of the sweep like the small ones. Systemic, so every rank takes the same branch.
@@ -391,6 +625,7 @@ ArrayRef dp_gemm(gadcu_comm* comm, const ArrayRef& a_in, const ArrayRef& b_in, M
     comm->no_peer_memory = true;
     return ArrayRef();
   }
+  if (comm->nvls && bytes % 16 == 0 && bytes <= comm->heap.grad_bytes) return dp_gemm_nvls(comm, g, rd, last);
   // GADCU_DP_PUSH = epilogue (default): the GEMM's epilogue stores each tile into its owner's staging buffer;
   //               = kernel: plain GEMM, then a scatter kernel on the communicator's stream
   static const bool push_from_epilogue = [] {
@@ -646,10 +881,21 @@ gadcu_status gadcu_comm_destroy(gadcu_comm* comm) {
   return guard([&] {
     if (!comm) return;
     if (comm->stream) { cudaStreamSynchronize(comm->stream); cudaStreamDestroy(comm->stream); }
-    for (int r = 0; r < comm->nranks; r++)
-      if (comm->heap.peer[r] && r != comm->rank) cudaIpcCloseMemHandle(comm->heap.peer[r]);
-    if (comm->heap.local) cudaFree(comm->heap.local);
+    cudaStreamSynchronize(comm->ctx->stream);
+    for (auto& b : comm->nv_slot_buf) {  // arrays that outlive the communicator take their data along
+      if (b && b->refs.load() > 1) {
+        std::shared_ptr<Pool> pool = comm->ctx->pool;
+        void* moved = pool->take(b->bytes);
+        cudaMemcpy(moved, b->ptr, b->bytes, cudaMemcpyDeviceToDevice);
+        b->ptr = moved;
+        b->pool = pool;
+      }
+      b.reset();
+    }
+    if (comm->heap.local) gadcu::symm_free(comm->heap.region);
     for (auto& e : comm->slot_done)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : comm->nv_slot_done)
       if (e) cudaEventDestroy(e);
     if (comm->comm) nccl().CommDestroy(comm->comm);
     delete comm;

@@ -421,7 +421,7 @@ Value EvalAlgebra::dot(const Value& a, const Value& b) {  // array.rs:119-126
   return Value(out);
 }
 
-ArrayRef EvalAlgebra::matmul_acc(ArrayRef acc, const ArrayRef& a_in, const ArrayRef& b_in, MatProp p1, MatProp p2) {
+ArrayRef EvalAlgebra::matmul_acc(ArrayRef acc, const ArrayRef& a_in, const ArrayRef& b_in, MatProp p1, MatProp p2, bool defer) {
   if (a_in->dtype != b_in->dtype) fail(GADCU_ERR_TYPE, "matmul: dtype mismatch");
   Dim4 rd = check::matmul(a_in->dims, b_in->dims, p1, p2);
   ArrayRef a = materialize(a_in), b = materialize(b_in);
@@ -443,6 +443,12 @@ ArrayRef EvalAlgebra::matmul_acc(ArrayRef acc, const ArrayRef& a_in, const Array
   g.strideC = rd[0] * rd[1];
   if (a->ptr() == a->buf->ptr) g.a_buf = a->buf.get();
   if (b->ptr() == b->buf->ptr) g.b_buf = b->buf.get();
+  // A product nothing is accumulated into, whose [M, N] result would be deferred elementwise territory anyway, is recorded
+  // rather than launched: what the layer does next to it (+ bias, tanh; the tanh VJP on an incoming dA; the residual of
+  // the square loss) then runs in the GEMM's epilogue (batched.cu: lazy_matmul / resolve_pending).
+  if (!acc && defer && ctx->gemm_epilogue && g.batch == 1 && g.dt == GADCU_F32 && lazy_enabled(ctx, rd.elements(), false) &&
+      k::gemm_epilogue_supported(g))
+    return lazy_matmul(ctx, a, b, p1, p2, rd);
   ArrayRef out;
   if (acc) {
     if (acc->dims != rd) fail(GADCU_ERR_DIMENSIONS, "Incompatible dimensions for add: " + acc->dims.str() + " " + rd.str());
@@ -467,7 +473,7 @@ ArrayRef EvalAlgebra::matmul_acc(ArrayRef acc, const ArrayRef& a_in, const Array
 Value EvalAlgebra::matmul(const Value& a, const Value& b, MatProp p1, MatProp p2) {  // matrix.rs:44-54
   require_data(a, "matmul");
   require_data(b, "matmul");
-  return Value(matmul_acc(ArrayRef(), a.data, b.data, p1, p2));
+  return Value(matmul_acc(ArrayRef(), a.data, b.data, p1, p2, /*defer=*/true));
 }
 Value EvalAlgebra::transpose(const Value& v, bool /*conjugate: identity on real types*/) {  // matrix.rs:57-60
   require_data(v, "transpose");

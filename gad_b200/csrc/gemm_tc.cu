@@ -432,7 +432,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                         const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, float* __restrict__ C,
                         uint32_t M, uint32_t N, uint32_t K, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t accumulate,
-                        OperandLayout la, OperandLayout lb, uint32_t band_m, uint32_t splits, const StreamK sk, const GemmPush push) {
+                        OperandLayout la, OperandLayout lb, uint32_t band_m, uint32_t splits, const StreamK sk, const GemmPush push,
+                        const GemmEpilogue epi) {
   using cfg = Cfg2<BKT, S>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -615,6 +616,10 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
         const uint32_t ncols = min(256u, N - nt * 256);
         float* crow = C + row + size_t(nt) * 256 * M;
         const bool add = head || accumulate, red = splits == 2;
+        // the fused elementwise tail runs where the product is complete: on whole units and on the HEAD of a split tile
+        // (the tail of a split tile stores its raw partial sum, which the head adds before transforming)
+        const int ek = w.part == 1 ? int(GemmEpilogue::NONE) : epi.kind;
+        const size_t elem0 = size_t(row) + size_t(nt) * 256 * M;  // (row, first column of the tile) in any [M, N] companion array
 #pragma unroll 1
         for (uint32_t c = 0; c < ncols; c += 32) {
           uint32_t r[32];
@@ -625,17 +630,59 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid
             for (int j = 0; j < 32; j++)
               if (uint32_t(j) < nj) cur[j] = __ldcg(crow + size_t(c + j) * M);  // (all in flight at once; L2, never a stale L1 line)
           }
-          tmem_ld32(taddr + c, r);
-          tmem_ld_wait();
-          if (row_ok) {
-            if (red) {
+          if (ek == GemmEpilogue::NONE) {
+            tmem_ld32(taddr + c, r);
+            tmem_ld_wait();
+            if (row_ok) {
+              if (red) {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                  if (uint32_t(j) < nj) atomicAdd(crow + size_t(c + j) * M, __uint_as_float(r[j]));  // (result unused: RED)
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                  if (uint32_t(j) < nj) crow[size_t(c + j) * M] = add ? cur[j] + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+              }
+            }
+          } else {
+            float aux[32];
+            if (ek != GemmEpilogue::BIAS_TANH && row_ok) {
 #pragma unroll
               for (int j = 0; j < 32; j++)
-                if (uint32_t(j) < nj) atomicAdd(crow + size_t(c + j) * M, __uint_as_float(r[j]));  // (result unused: RED)
-            } else {
+                if (uint32_t(j) < nj) aux[j] = __ldcs(epi.aux + elem0 + size_t(c + j) * M);
+            }
+            // this chunk's 32 bias values: lane j holds column c + j's, handed round by shuffle
+            float bias_mine = 0.0f;
+            if (ek != GemmEpilogue::TANH_GRAD && uint32_t(lane) < nj) bias_mine = __ldg(epi.bias + nt * 256 + c + lane);
+            tmem_ld32(taddr + c, r);
+            tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (uint32_t(j) < nj) crow[size_t(c + j) * M] = add ? cur[j] + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+            for (int j = 0; j < 32; j++) {
+              const float b = __shfl_sync(0xffffffffu, bias_mine, j);
+              if (row_ok && uint32_t(j) < nj) {
+                float v = add ? cur[j] + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+                // (this translation unit is compiled with -fmad=false: every operation below rounds on its own, as the
+                // tape's separate kernels do)
+                if (ek == GemmEpilogue::BIAS_TANH) {
+                  v = tanhf(v + b);
+                } else if (ek == GemmEpilogue::TANH_GRAD) {
+                  const float t = aux[j], s = t * t, n = 0.0f - s, e = n + 1.0f;
+                  v = v * e;
+                } else {
+                  const float zb = v + b;
+                  v = aux[j] - zb;
+                }
+                const size_t at = size_t(c + j) * M;
+                crow[at] = v;
+                if (epi.hi) {
+                  uint32_t t32;
+                  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t32) : "f"(v));
+                  const float h = __uint_as_float(t32);
+                  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t32) : "f"(v - h));
+                  epi.hi[elem0 + at] = h;
+                  epi.lo[elem0 + at] = __uint_as_float(t32);
+                }
+              }
             }
           }
         }
@@ -695,6 +742,30 @@ __global__ void __launch_bounds__(256) split_tf32_pad_kernel(const float* __rest
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v - h));
     hi[i] = h;
     lo[i] = __uint_as_float(t);
+  }
+}
+
+// out = w + d (WeightOps::add_assign, gad/src/net.rs:171-175) with the TF32 split of the sum written in the same pass:
+// the weight matrix is a GEMM operand of the next step, which then finds its [hi | lo] copy ready instead of spending a
+// 12 B/element pass on it (8 B/element extra here: the sum is already in registers)
+__global__ void __launch_bounds__(256) add_split_tf32_kernel(const float4* __restrict__ w, const float4* __restrict__ d, float4* __restrict__ out,
+                                                             float4* __restrict__ hi, float4* __restrict__ lo, uint64_t nvec) {
+  const uint64_t stride = uint64_t(gridDim.x) * 256;
+  for (uint64_t i = uint64_t(blockIdx.x) * 256 + threadIdx.x; i < nvec; i += stride) {
+    const float4 a = w[i], b = __ldcs(d + i);
+    float4 v, h, l;
+    v.x = a.x + b.x; v.y = a.y + b.y; v.z = a.z + b.z; v.w = a.w + b.w;
+    uint32_t t;
+#define GADCU_SPLIT(c)                                                      \
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.c));                     \
+  h.c = __uint_as_float(t);                                                 \
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.c - h.c));               \
+  l.c = __uint_as_float(t);
+    GADCU_SPLIT(x) GADCU_SPLIT(y) GADCU_SPLIT(z) GADCU_SPLIT(w)
+#undef GADCU_SPLIT
+    out[i] = v;
+    hi[i] = h;
+    lo[i] = l;
   }
 }
 
@@ -818,7 +889,7 @@ struct PairPlan {
   uint32_t num_kb;              // k-blocks per tile
 };
 PairPlan plan_pair(int sm_count, bool comm_inflight, uint64_t M, uint64_t N, uint64_t K, int bkt, bool accumulate,
-                   int push_splits /* 0: not the tile-pushing mode */, bool have_flags) {
+                   int push_splits /* 0: not the tile-pushing mode */, bool have_flags, bool no_split = false /* an epilogue rides along: no red.add halves */) {
   PairPlan p{};
   const uint64_t tiles = ((M + 255) / 256) * ((N + 255) / 256);
   // while an overlapped all-reduce is in flight a few SM pairs are left to its CTAs (a persistent CTA per SM would
@@ -844,7 +915,7 @@ PairPlan plan_pair(int sm_count, bool comm_inflight, uint64_t M, uint64_t N, uin
     const bool lone_wide_wave = tiles < p.clusters && tiles * 2 > p.clusters;
     if (tail >= min_tail && gain >= 0.03 && !lone_wide_wave) p.rem = uint32_t(rem), p.tail_kb = uint32_t(tail);
   }
-  p.splits = push_splits ? uint32_t(push_splits) : (streamk ? 1u : choose_splits_for(sm_count, M, N, K, accumulate, bkt));  // (push: the exchange laid its staging out for this)
+  p.splits = push_splits ? uint32_t(push_splits) : ((streamk || no_split) ? 1u : choose_splits_for(sm_count, M, N, K, accumulate, bkt));  // (push: the exchange laid its staging out for this)
   // band of tiles whose operand slices (hi + lo, 8 bytes per element) should fit in about half of L2 (126 MB), along
   // the dimension with the smaller operand: that operand is then read from HBM once, the other once per band
   static const uint32_t band_override = [] { const char* e = getenv("GADCU_GEMM_BAND"); return e ? uint32_t(atoi(e)) : 0u; }();
@@ -871,7 +942,7 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   CUtensorMap mah = make_map(ah, a_mn, a_mn_ext, a_k_ext, lda, 128, BKT, k_swz), mal = make_map(al, a_mn, a_mn_ext, a_k_ext, lda, 128, BKT, k_swz);
   CUtensorMap mbh = make_map(bh, b_mn, b_mn_ext, b_k_ext, ldb, 128, BKT, k_swz), mbl = make_map(bl, b_mn, b_mn_ext, b_k_ext, ldb, 128, BKT, k_swz);
   const PairPlan plan = plan_pair(ctx->sm_count, ctx->comm_inflight.load(std::memory_order_relaxed), g.M, g.N, g.K, BKT, g.accumulate,
-                                  g.push ? int(g.push->splits) : 0, ctx->gemm_flags != nullptr);
+                                  g.push ? int(g.push->splits) : 0, ctx->gemm_flags != nullptr, g.epi != nullptr);
   const uint64_t clusters = plan.clusters;
   StreamK sk{plan.rem, plan.tail_kb, ctx->gemm_flags, nullptr};
   static const int trace_at = [] { const char* e = getenv("GADCU_SK_TRACE"); return e ? atoi(e) : 0; }();  // trace the n-th launch
@@ -889,7 +960,7 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
   });
   gemm_tf32x3_pair_kernel<BKT, S><<<unsigned(2 * clusters), kThreads2, Cfg2<BKT, S>::kSmem, ctx->stream>>>(
       mah, mal, mbh, mbl, static_cast<float*>(g.C), uint32_t(g.M), uint32_t(g.N), uint32_t(g.K), a_mn, b_mn, g.accumulate, la, lb, band_arg,
-      splits, sk, g.push ? *g.push : GemmPush{});
+      splits, sk, g.push ? *g.push : GemmPush{}, g.epi ? *g.epi : GemmEpilogue{});
   if (trace_on) {
     cudaStreamSynchronize(ctx->stream);
     unsigned long long t0 = ~0ull;
@@ -916,8 +987,15 @@ void launch_pair(gadcu_ctx* ctx, const GemmArgs& g, const float* ah, const float
 static const float* split_operand(gadcu_ctx* ctx, const float* x, uint64_t R, uint64_t C, Buffer* owner, ArrayRef& keep, uint64_t& ld) {
   ld = (R + 31) / 32 * 32;
   const uint64_t elems = ld * C;
+  // The split is a function of the buffer's contents alone: it stays valid until the buffer is written in place
+  // (Buffer::mutated drops it) or dies. Activations and gradients die with their tape, so their copies go with them; a
+  // weight matrix keeps its copy across steps for as long as nothing updates it, and WeightOps::add_assign — the one
+  // thing that does — refreshes the copy in the same pass (add_assign_refresh_split below). GADCU_SPLIT_CACHE=tape
+  // restores round 1's rule (a copy is trusted only within the tape that made it).
+  static const bool per_tape = [] { const char* e = getenv("GADCU_SPLIT_CACHE"); return e && std::string(e) == "tape"; }();
   const uint64_t epoch = ctx->epoch.load(std::memory_order_relaxed);
-  if (owner && owner->split && owner->split_epoch == epoch && owner->split_elems == elems && owner->split_rows == R)
+  // (not while a CUDA graph is being captured: the replayed graph must redo the split of whatever the buffer holds then)
+  if (!ctx->capturing && owner && owner->split && (!per_tape || owner->split_epoch == epoch) && owner->split_elems == elems && owner->split_rows == R)
     return static_cast<const float*>(owner->split->ptr);
   keep = new_array(ctx, GADCU_F32, Dim4(2 * elems));
   float* hi = static_cast<float*>(keep->ptr());
@@ -964,7 +1042,44 @@ size_t gemm_schedule_debug(int sm_count, uint64_t M, uint64_t N, uint64_t K, int
   return n;
 }
 
+// `dst` (the buffer the sum goes to: `src` itself for an in-place update, a fresh one for a copy-on-write one) receives
+// src + d and, if `src` carried a current, unpadded TF32 split, a refreshed split of the sum. Returns false (nothing
+// launched) when that does not apply and the caller should do the plain add.
+bool add_assign_refresh_split(gadcu_ctx* ctx, Buffer* src, const float* d, Buffer* dst, uint64_t n) {
+  if (!src->split || src->split_elems != n || src->split_rows % 32 != 0 || n % 4 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(src->ptr) | reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(dst->ptr)) & 15) return false;
+  Buffer* split = src->split;  // [hi | lo], 2 n floats
+  ArrayRef fresh;
+  if (dst != src || split->refs.load() > 1) {  // (a GEMM still in flight may hold the old copy: stream order covers reads, but a new buffer is simplest)
+    fresh = new_array(ctx, GADCU_F32, Dim4(2 * n));
+    split = fresh->buf.get();
+  }
+  float* hi = static_cast<float*>(split->ptr);
+  const uint64_t nvec = n / 4;
+  const uint64_t blocks = std::min<uint64_t>((nvec + 255) / 256, uint64_t(ctx->sm_count) * 8);
+  add_split_tf32_kernel<<<unsigned(blocks), 256, 0, ctx->stream>>>(static_cast<const float4*>(src->ptr), reinterpret_cast<const float4*>(d),
+                                                                  static_cast<float4*>(dst->ptr), reinterpret_cast<float4*>(hi),
+                                                                  reinterpret_cast<float4*>(hi + n), nvec);
+  ctx->count_launch();
+  const uint64_t rows = src->split_rows;
+  if (fresh) {
+    dst->mutated();
+    dst->split = split;
+    split->retain();
+  }
+  dst->split_elems = n;
+  dst->split_rows = rows;
+  dst->split_epoch = ctx->epoch.load(std::memory_order_relaxed);
+  return true;
+}
+
 uint32_t gemm_push_splits(gadcu_ctx* ctx, const GemmArgs& g) { return choose_splits(ctx, g, pair_variant() == 1 ? 32 : 16); }
+
+bool gemm_epilogue_supported(const GemmArgs& g) {
+  if (!gemm_tc_supported(g) || pair_variant() == 0 || g.accumulate || g.push) return false;
+  const bool ragged = g.M % 128 != 0 || g.N % 128 != 0 || g.K % BK != 0;
+  return ragged || (g.M % 256 == 0 && g.N % 256 == 0);  // the shapes launch_gemm_tc gives to the pair kernel
+}
 
 bool gemm_push_supported(const GemmArgs& g) {
   return gemm_tc_supported(g) && pair_variant() != 0 && g.M % 256 == 0 && g.N % 256 == 0 && !g.accumulate;
@@ -988,6 +1103,7 @@ void launch_gemm_tc(gadcu_ctx* ctx, const GemmArgs& g) {
     }
   } else {
     if (g.push) fail(GADCU_ERR_UNSUPPORTED, "gemm: the tile-pushing epilogue needs M and N to be multiples of 256");
+    if (g.epi) fail(GADCU_ERR_UNSUPPORTED, "gemm: a fused elementwise epilogue needs the pair kernel (gemm_epilogue_supported)");
     const OperandLayout mn_layout{BK * 128u, 512u, 1024u, 1u};
     const OperandLayout k_layout{16u, 1024u, UMMA_K * 4u, 2u};
     const OperandLayout la = a_mn ? mn_layout : k_layout, lb = b_mn ? mn_layout : k_layout;

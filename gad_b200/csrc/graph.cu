@@ -576,7 +576,7 @@ void GraphAlgebra::vjp(const Node& n, Algebra& ga, Store& store, const Value& g)
           ArrayRef cur;
           if (it != store.values.end()) cur = std::move(it->second.data);
           ArrayRef sunk = (cur || same_operand) ? ArrayRef() : try_gemm_sink(v1.id, lhs.data, rhs.data, pl, pr);
-          store.values[v1.id] = Value(sunk ? sunk : ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr));
+          store.values[v1.id] = Value(sunk ? sunk : ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr, /*defer=*/!is_variable(v1.id)));
         } else {
           Value l = fix1 ? ga.link(lhs) : lhs, r = fix1 ? rhs : ga.link(rhs);
           Value grad = ga.matmul(l, r, pl, pr);
@@ -592,7 +592,7 @@ void GraphAlgebra::vjp(const Node& n, Algebra& ga, Store& store, const Value& g)
           ArrayRef cur;
           if (it != store.values.end()) cur = std::move(it->second.data);
           ArrayRef sunk = (cur || same_operand) ? ArrayRef() : try_gemm_sink(v2.id, lhs.data, rhs.data, pl, pr);
-          store.values[v2.id] = Value(sunk ? sunk : ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr));
+          store.values[v2.id] = Value(sunk ? sunk : ev->matmul_acc(std::move(cur), lhs.data, rhs.data, pl, pr, /*defer=*/!is_variable(v2.id)));
         } else {
           Value l = fix2 ? lhs : ga.link(lhs), r = fix2 ? ga.link(rhs) : rhs;
           Value grad = ga.matmul(l, r, pl, pr);

@@ -80,6 +80,23 @@ struct GemmPush {
   uint32_t splits = 1;  // partial blocks per (tile, rank): 2 when the GEMM splits its k range (gemm_push_splits)
 };
 
+// An elementwise tail evaluated in the GEMM's epilogue, on the accumulator while it is still in registers, instead of by
+// a separate pass over C (SURVEY §2.1 "epilogue fusions"): the chains an MLP layer puts right behind its products. Each
+// is the exact op sequence the tape would run as separate kernels — one rounding per op, no contraction — so the
+// fused and the unfused sweep agree bit for bit (tests/test_gpu_epilogue.py).
+//   BIAS_TANH     out = tanh(acc + bias[col])               add(matmul, tile_as(b)) -> tanh   (core.rs:179-182, analytic.rs:96-98)
+//   TANH_GRAD     out = acc * ((0 - t*t) + 1), t = aux      the tanh VJP on an incoming dA    (analytic.rs:385-395)
+//   BIAS_RESIDUAL out = aux - (acc + bias[col])             SquareLoss: sub(target, add(matmul, tile_as(b)))  (net_ext.rs:110-118)
+// With hi / lo set the TF32 split of `out` (the operand copies the next tensor-core GEMM reads) is written in the same pass.
+struct GemmEpilogue {
+  enum Kind : int { NONE = 0, BIAS_TANH = 1, TANH_GRAD = 2, BIAS_RESIDUAL = 3 };
+  int kind = NONE;
+  const float* bias = nullptr;  // [N]
+  const float* aux = nullptr;   // [M, N] column-major, leading dimension M
+  float* hi = nullptr;          // [M, N], leading dimension M (needs M % 32 == 0), or null
+  float* lo = nullptr;
+};
+
 // C[M,N] (+)= op(A) * op(B), column-major; batch over `batch` matrices with element strides (0 = broadcast).
 struct GemmArgs {
   gadcu_dtype dt = GADCU_F32;
@@ -94,11 +111,15 @@ struct GemmArgs {
   Buffer* a_buf = nullptr;    // owning buffers when an operand is a whole dense buffer (TF32 split cache)
   Buffer* b_buf = nullptr;
   const GemmPush* push = nullptr;  // tensor-core pair kernel only (M, N multiples of 256)
+  const GemmEpilogue* epi = nullptr;  // tensor-core pair kernel only (gemm_epilogue_supported)
 };
 void launch_gemm(gadcu_ctx* ctx, const GemmArgs& g);
 bool gemm_tc_supported(const GemmArgs& g);  // tcgen05 3xTF32 path applies
+bool gemm_epilogue_supported(const GemmArgs& g);  // ... and its CTA-pair kernel would run it, so an epilogue can ride along
 bool gemm_push_supported(const GemmArgs& g);  // ... and its CTA-pair kernel, which can push tiles to peers
 size_t gemm_schedule_debug(int sm_count, uint64_t M, uint64_t N, uint64_t K, int push_splits, uint32_t* rows, size_t cap, uint32_t* info);  // gemm_tc.cu
+// dst = src + d with the cached TF32 split of `src` refreshed for the sum in the same pass (gemm_tc.cu); false: not applicable
+bool add_assign_refresh_split(gadcu_ctx* ctx, Buffer* src, const float* d, Buffer* dst, uint64_t n);
 uint32_t gemm_push_splits(gadcu_ctx* ctx, const GemmArgs& g);  // 1 or 2: how the pair kernel would split k for this shape
 
 }  // namespace k

@@ -198,6 +198,10 @@ gadcu_status gadcu_ctx_set_lazy(gadcu_ctx* ctx, int enable, uint64_t min_element
   ctx->lazy_threshold = min_elements < 2 ? 2 : min_elements;  // single elements (gad's scalars) always run eagerly
   return GADCU_OK;
 }
+gadcu_status gadcu_ctx_set_gemm_epilogue(gadcu_ctx* ctx, int enable) {
+  ctx->gemm_epilogue = enable != 0;
+  return GADCU_OK;
+}
 gadcu_status gadcu_ctx_set_strict_reference(gadcu_ctx* ctx, int strict) {
   ctx->strict_reference = strict != 0;
   return GADCU_OK;
@@ -351,7 +355,14 @@ gadcu_status gadcu_array_add_assign(gadcu_array* self, const gadcu_array* other)
     const bool shared = self->buf->refs.load() > 1;
     ArrayRef fresh;
     if (shared) fresh = new_array(self->ctx, self->dtype, self->dims, self->is_scalar);
-    else self->buf->mutated();
+    // a weight matrix that feeds tensor-core GEMMs carries its TF32 [hi | lo] copy: refresh it in the same pass
+    if (self->dtype == GADCU_F32 && !other_dense->bcast1() && !other_dense->lazy() &&
+        k::add_assign_refresh_split(self->ctx, self->buf.get(), static_cast<const float*>(other_dense->ptr()), shared ? fresh->buf.get() : self->buf.get(),
+                                    self->elements())) {
+      if (shared) self->buf = fresh->buf;
+      return;
+    }
+    if (!shared) self->buf->mutated();
     k::EwArgs e;
     e.dt = self->dtype; e.nin = 2; e.in[0] = self->ptr(); e.in[1] = other_dense->ptr(); e.bcast[1] = other_dense->bcast1();
     e.out = shared ? fresh->ptr() : self->ptr();

