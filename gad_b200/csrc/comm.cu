@@ -288,7 +288,14 @@ void ensure_heap(gadcu_comm* comm, size_t bytes) {
   if (comm->nranks > 8) fail(GADCU_ERR_UNSUPPORTED, "data-parallel exchange: at most 8 ranks");
   gadcu_ctx* ctx = comm->ctx;
   SymmHeap& h = comm->heap;
-  static const bool want_nvls = [] { const char* e = getenv("GADCU_DP_NVLS"); return !e || atoi(e) != 0; }();
+  // GADCU_DP_NVLS = auto (default) | 1 | 0. The switch-side reduction moves (1 + 1/N) S bytes per direction and GPU where the
+  // tile-pushing exchange moves 2 (N-1)/N S: fewer from 4 ranks on, more at 2 — and it leaves the GEMMs alone. Measured
+  // (steps/s, C4, one call each): 2 GPUs 206.6 vs 210.1 pushing, 4 GPUs 370.4 vs 361.6, 8 GPUs 635.1 vs 585.2.
+  const bool want_nvls = [&] {
+    const char* e = getenv("GADCU_DP_NVLS");
+    if (!e || std::string(e) == "auto") return comm->nranks >= 4;
+    return atoi(e) != 0;
+  }();
   const size_t grad = (bytes + 255) / 256 * 256;
   const size_t legacy_slot = 2 * grad;  // (a k-split GEMM pushes two partial blocks per tile and rank)
   const size_t data = std::max(size_t(2 * kSlots) * legacy_slot, size_t(kSlotsNv) * grad);
@@ -393,9 +400,12 @@ void nvls_allreduce_cfg(gadcu_comm* comm, size_t byte_offset, size_t bytes, unsi
 void nvls_allreduce(gadcu_comm* comm, size_t byte_offset, size_t bytes) {
   static const unsigned blocks = [] {
     const char* e = getenv("GADCU_NVLS_BLOCKS");
-    return unsigned(std::max(1, std::min(kNvlsMaxBlocks, e ? atoi(e) : 64)));
+    // 8 blocks already run the fabric at its rate (measured alone, 8 ranks, 64 MiB: 0.166 ms with 8 blocks, 0.18 with 64)
+    // and leave the SMs to the GEMMs the exchange overlaps
+    return unsigned(std::max(1, std::min(kNvlsMaxBlocks, e ? atoi(e) : 8)));
   }();
-  static const int unroll = [] { const char* e = getenv("GADCU_NVLS_UNROLL"); return e ? atoi(e) : 8; }();
+  // (4 in flight: 32 registers x 512 threads fit beside the GEMM's CTA on an SM; 8 would not)
+  static const int unroll = [] { const char* e = getenv("GADCU_NVLS_UNROLL"); return e ? atoi(e) : 4; }();
   nvls_allreduce_cfg(comm, byte_offset, bytes, blocks, unroll);
 }
 // GADCU_NVLS_BENCH=1: right after the heap is up, time the exchange kernel alone over one slot for a grid of launch shapes
@@ -561,7 +571,9 @@ ArrayRef dp_gemm_nvls(gadcu_comm* comm, const k::GemmArgs& g, const Dim4& rd, bo
   ArrayRef out(arr, false);
   // the sweep's LAST gradient has nothing left to hide behind: cut into column chunks, the exchange of one chunk overlaps
   // the GEMM of the next and only the last chunk's exchange is exposed
-  static const uint64_t max_chunks = [] { const char* e = getenv("GADCU_DP_TAIL_CHUNKS"); return e ? uint64_t(std::max(1, atoi(e))) : uint64_t(2); }();
+  // (measured, 8 GPUs: 2 chunks 595 steps/s vs 635 whole — the half-width GEMMs and the exchange running beside the second
+  // one cost more than the overlap buys; GADCU_DP_TAIL_CHUNKS=2|4 to try)
+  static const uint64_t max_chunks = [] { const char* e = getenv("GADCU_DP_TAIL_CHUNKS"); return e ? uint64_t(std::max(1, atoi(e))) : uint64_t(1); }();
   uint64_t chunks = 1;
   if (last && !g.tb)
     while (chunks * 2 <= max_chunks && g.N % (chunks * 2 * 256) == 0 && (bytes / (chunks * 2)) % (16 * 8) == 0) chunks *= 2;
