@@ -694,9 +694,24 @@ def replay_metric(ctx, ext, torch, gb, wl):
         e0.record(ext)
         for _ in range(reps):
             fn()
+        ctx.flush()  # (auto replay: what the last call recorded reaches the stream before the closing event)
         e1.record(ext)
         e1.synchronize()
         return e0.elapsed_time(e1) / reps
+
+    def auto_time(fn, reps):
+        """The same plain calls with gadcu_ctx_set_auto_replay on: every step rebuilds its tape; what it issues runs as one
+        graph laid over the last step's."""
+        ctx.set_auto_replay(True)
+        try:
+            for _ in range(5):
+                fn()
+            s0 = ctx.replay_stats()
+            ms = ev_time(fn, reps)
+            s1 = ctx.replay_stats()
+        finally:
+            ctx.set_auto_replay(False)
+        return ms, {k: s1[k] - s0[k] for k in s0}
 
     res = {}
     B_, D_ = 512, 256
@@ -718,8 +733,13 @@ def replay_metric(ctx, ext, torch, gb, wl):
         cap.launch()
     ms_replay = ev_time(cap.launch, 200)
     same = captured[0].item() == keep["e"][0].item()
+    ms_auto, auto_stats = auto_time(eager, 200)
     res["mlp_small"] = {"workload": f"C4-shaped step at B={B_}, D={D_}, L={L}, f32", "eager_ms": ms_eager, "replay_ms": ms_replay,
-                        "eager_steps_per_s": 1e3 / ms_eager, "replay_steps_per_s": 1e3 / ms_replay, "loss_identical": bool(same)}
+                        "auto_replay_ms": ms_auto, "auto_replay_segments": auto_stats,
+                        "eager_steps_per_s": 1e3 / ms_eager, "replay_steps_per_s": 1e3 / ms_replay, "auto_replay_steps_per_s": 1e3 / ms_auto,
+                        "loss_identical": bool(same), "auto_loss_identical": bool(keep["e"][0].item() == captured[0].item()),
+                        "note": "replay = an explicit gadcu_capture of one step launched again; auto_replay = plain wl.mlp_step calls (a fresh Graph1 each) "
+                                "with gadcu_ctx_set_auto_replay: the recorded kernel sequence is the structural key"}
     del cap, captured
     n = 1 << 16
     x = ctx.random((n,), 3, a=-1.0, b=1.0)
@@ -736,8 +756,11 @@ def replay_metric(ctx, ext, torch, gb, wl):
     for _ in range(5):
         cap3.launch()
     ms_replay3 = ev_time(cap3.launch, 200)
+    z_eager = keep["c3"][0].item()
+    ms_auto3, auto_stats3 = auto_time(eager3, 200)
     res["c3_small"] = {"workload": f"C3 tape at n={n}, f32, forward + reverse sweep", "eager_ms": ms_eager3, "replay_ms": ms_replay3,
-                       "z_identical": bool(captured3[0].item() == keep["c3"][0].item())}
+                       "auto_replay_ms": ms_auto3, "auto_replay_segments": auto_stats3,
+                       "z_identical": bool(captured3[0].item() == z_eager), "auto_z_identical": bool(keep["c3"][0].item() == z_eager)}
     return res
 
 

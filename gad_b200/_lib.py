@@ -63,6 +63,9 @@ SIGNATURES = {
     "gadcu_ctx_set_fusion": (C.c_int, [P, C.c_int]),
     "gadcu_ctx_set_strict_reference": (C.c_int, [P, C.c_int]),
     "gadcu_ctx_set_gemm_epilogue": (C.c_int, [P, C.c_int]),
+    "gadcu_ctx_set_auto_replay": (C.c_int, [P, C.c_int]),
+    "gadcu_ctx_flush": (C.c_int, [P]),
+    "gadcu_ctx_replay_stats": (C.c_int, [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gadcu_ctx_memory_stats": (C.c_int, [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gadcu_ctx_profile_begin": (C.c_int, [P]),
     "gadcu_ctx_profile_end": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

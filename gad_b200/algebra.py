@@ -143,6 +143,20 @@ class Context:
         """Deferred elementwise regions (gadcu_ctx_set_lazy): on by default for arrays of >= 32768 elements."""
         _check(self.lib.gadcu_ctx_set_lazy(self.handle, int(enable), int(min_elements)))
 
+    def set_auto_replay(self, enable: bool) -> None:
+        """Automatic CUDA-graph replay keyed by tape structure (gadcu_ctx_set_auto_replay): launches are recorded and run as
+        one graph at the next read / synchronise / end of a reverse sweep, re-using the executable graph of the last step
+        with the same kernel sequence. Off by default."""
+        _check(self.lib.gadcu_ctx_set_auto_replay(self.handle, int(enable)))
+
+    def flush(self) -> None:
+        _check(self.lib.gadcu_ctx_flush(self.handle))
+
+    def replay_stats(self) -> dict:
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self.lib.gadcu_ctx_replay_stats(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return {"segments": a.value, "reused": b.value, "instantiated": c.value}
+
     def set_gemm_epilogue(self, enable: bool) -> None:
         """Fused GEMM epilogues (gadcu_ctx_set_gemm_epilogue): on by default; off = every product launched where it is recorded."""
         _check(self.lib.gadcu_ctx_set_gemm_epilogue(self.handle, int(enable)))

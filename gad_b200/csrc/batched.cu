@@ -439,6 +439,7 @@ std::vector<ArrayRef> SymProgram::run_interpreter(const std::vector<int32_t>& to
   std::memcpy(host.data(), dev.data(), prog_bytes);
   std::memcpy(host.data() + align(prog_bytes), in_ptrs.data(), in_ptrs.size() * sizeof(void*));
   std::memcpy(host.data() + align(prog_bytes) + align(in_bytes), out_ptrs.data(), out_ptrs.size() * sizeof(void*));
+  ctx->segment_flush();
   GADCU_CUDA(cudaMemcpyAsync(blob->ptr(), host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream));
   GADCU_CUDA(cudaStreamSynchronize(ctx->stream));  // `host` is pageable
   char* base = static_cast<char*>(blob->ptr());
@@ -1049,6 +1050,7 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   auto build = [&](const std::string& k) {
     const jit::Kernel* kernel = jit::find(k);
     if (!kernel) {
+      ctx->segment_flush();  // (compiling and loading a module is not something to do inside a recorded segment)
       g_plan = &J;
       const std::string src = gen_source(*this, J, imm_slot);
       g_plan = nullptr;

@@ -229,6 +229,7 @@ gadcu_status gadcu_evaluate_gradients(gadcu_algebra* g, uint32_t arena, uint32_t
       *out = batched_evaluate_gradients(*graph, Id{arena, index}, ArrayRef(seed, true), once != 0).release();
     else
       *out = graph->evaluate_gradients(Id{arena, index}, ArrayRef(seed, true), once != 0).release();
+    g->ctx->segment_flush();  // auto replay: a finished sweep is where a step's recorded launches run (as one graph)
   });
 }
 gadcu_status gadcu_compute_gradients(gadcu_algebra* g, uint32_t arena, uint32_t index, const gadcu_value* seed, gadcu_store** out) {
@@ -237,6 +238,7 @@ gadcu_status gadcu_compute_gradients(gadcu_algebra* g, uint32_t arena, uint32_t 
     auto* graph = dynamic_cast<GraphAlgebra*>(g);
     if (!graph) fail(GADCU_ERR_INVALID, "compute_gradients needs a GraphN algebra");
     *out = graph->compute_gradients(Id{arena, index}, in_value(seed)).release();
+    g->ctx->segment_flush();
   });
 }
 gadcu_status gadcu_store_get(const gadcu_store* s, uint32_t arena, uint32_t index, gadcu_value* out, int* found) {

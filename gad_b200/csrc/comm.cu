@@ -170,6 +170,7 @@ bool small_allreduce(gadcu_comm* comm, gadcu_array* const* arrays, size_t n);
 gadcu_status gadcu_comm_allreduce_sum(gadcu_comm* comm, gadcu_array* const* arrays, size_t n) {
   return guard([&] {
     if (comm->nranks <= 1) return;
+    comm->ctx->segment_flush();
     for (size_t i = 0; i < n; i++)
       if (arrays[i]->symbolic()) materialize(ArrayRef(arrays[i], true));
     if (small_allreduce(comm, arrays, n)) return;  // once the peer-memory exchange is up, small arrays use it too
@@ -757,6 +758,7 @@ void join(gadcu_comm* comm) {
 gadcu_status gadcu_comm_allreduce_sum_async(gadcu_comm* comm, gadcu_array* const* arrays, size_t n) {
   return guard([&] {
     if (comm->nranks <= 1) return;
+    comm->ctx->segment_flush();
     for (size_t i = 0; i < n; i++) allreduce_async(comm, ArrayRef(arrays[i], true));
   });
 }
@@ -780,6 +782,12 @@ gadcu_status gadcu_evaluate_gradients_dp_with(gadcu_algebra* g, uint32_t arena, 
     auto* graph = dynamic_cast<GraphAlgebra*>(g);
     if (!graph || graph->kind() != GADCU_GRAPH1) fail(GADCU_ERR_INVALID, "evaluate_gradients_dp needs a Graph1 algebra");
     const bool dp = comm && comm->nranks > 1;
+    const bool was_auto = g->ctx->auto_replay;
+    if (dp) {  // the exchange interleaves streams and cross-rank barriers with the sweep: it is issued eagerly
+      g->ctx->segment_flush();
+      g->ctx->auto_replay = false;
+    }
+    struct Restore { gadcu_ctx* c; bool v; ~Restore() { c->auto_replay = v; } } restore{g->ctx, was_auto};
     // GADCU_DP = fused (default): GEMM-produced gradients are reduce-scattered by the GEMM epilogue over peer memory
     // and gathered on the communicator's stream while the sweep continues; everything else (biases) goes through
     // one grouped NCCL all-reduce at the end. GADCU_DP = nccl-overlap: every gradient through NCCL as soon as final.
@@ -867,6 +875,12 @@ gadcu_status gadcu_compute_gradients_dp(gadcu_algebra* g, uint32_t arena, uint32
     if (!seed) fail(GADCU_ERR_INVALID, "null seed");
     const Value sv(ArrayRef(seed->data, true), Id{seed->arena, seed->index});
     const bool dp = comm && comm->nranks > 1;
+    const bool was_auto = g->ctx->auto_replay;
+    if (dp) {
+      g->ctx->segment_flush();
+      g->ctx->auto_replay = false;
+    }
+    struct Restore { gadcu_ctx* c; bool v; ~Restore() { c->auto_replay = v; } } restore{g->ctx, was_auto};
     if (dp)
       graph->set_final_hook([comm](Id, const ArrayRef& grad_in) -> ArrayRef {
         ArrayRef dense = materialize(grad_in);

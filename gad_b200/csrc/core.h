@@ -122,9 +122,28 @@ struct gadcu_ctx {
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[4];
 
+  // ---- automatic CUDA-graph replay keyed by tape structure (gadcu_ctx_set_auto_replay; runtime.cu) -----------------
+  // A gad program rebuilds its tape every step (net_ext.rs:52), so there is no object to attach a captured graph to — but
+  // the kernels a step issues are the same sequence every time. With auto replay on, the context's stream records what
+  // is issued (a capture SEGMENT) instead of launching it; a segment ends where the host needs results or order (a read, a
+  // synchronise, an upload, a collective, the end of a reverse sweep) and is then run as ONE graph launch: the segment's
+  // graph is laid over an executable graph of the same shape kept from an earlier step (cudaGraphExecUpdate: same kernels,
+  // same order, new pointers and scalars), or instantiated if there is none. The structural key is the captured sequence
+  // itself; nothing is assumed about the program.
+  bool auto_replay = false;
+  bool segment_open = false;
+  uint32_t segment_launches = 0;
+  std::multimap<size_t, cudaGraphExec_t> replay_execs;  // by node count
+  uint64_t replay_segments = 0, replay_hits = 0, replay_misses = 0;
+  void segment_begin();  // before anything is issued on `stream` (no-op unless auto replay applies)
+  void segment_flush();  // run what has been recorded
+
   std::shared_ptr<gadcu::Pool> active_pool() { return capturing && capture_pool ? capture_pool : pool; }
   void* scratch(size_t bytes);
-  void count_launch(uint64_t n = 1) { launches.fetch_add(n, std::memory_order_relaxed); }
+  void count_launch(uint64_t n = 1) {
+    launches.fetch_add(n, std::memory_order_relaxed);
+    if (segment_open && (segment_launches += uint32_t(n)) >= 512) segment_flush();  // (a long eval-only stretch: do not sit on it)
+  }
 };
 
 namespace gadcu {
@@ -136,6 +155,7 @@ struct ProfileScope {
   int cat;
   cudaEvent_t start = nullptr;
   ProfileScope(gadcu_ctx* c, int category) : ctx(c), cat(category) {
+    ctx->segment_begin();  // (every launch helper opens with one of these)
     if (ctx->profiling && !ctx->capturing) {
       cudaEventCreate(&start);
       cudaEventRecord(start, ctx->stream);

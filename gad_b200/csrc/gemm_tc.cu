@@ -1057,6 +1057,7 @@ bool add_assign_refresh_split(gadcu_ctx* ctx, Buffer* src, const float* d, Buffe
   float* hi = static_cast<float*>(split->ptr);
   const uint64_t nvec = n / 4;
   const uint64_t blocks = std::min<uint64_t>((nvec + 255) / 256, uint64_t(ctx->sm_count) * 8);
+  ctx->segment_begin();
   add_split_tf32_kernel<<<unsigned(blocks), 256, 0, ctx->stream>>>(static_cast<const float4*>(src->ptr), reinterpret_cast<const float4*>(d),
                                                                   static_cast<float4*>(dst->ptr), reinterpret_cast<float4*>(hi),
                                                                   reinterpret_cast<float4*>(hi + n), nvec);

@@ -57,6 +57,66 @@ void Pool::put(void* p, size_t bytes) {
   in_use -= bytes;
 }
 
+}  // namespace gadcu
+
+void gadcu_ctx::segment_begin() {
+  if (!auto_replay || capturing || profiling || segment_open) return;
+  if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    return;  // (issue eagerly)
+  }
+  segment_open = true;
+  segment_launches = 0;
+}
+
+void gadcu_ctx::segment_flush() {
+  if (!segment_open) return;
+  segment_open = false;
+  cudaGraph_t graph = nullptr;
+  const cudaError_t err = cudaStreamEndCapture(stream, &graph);
+  if (err != cudaSuccess || !graph) {
+    cudaGetLastError();
+    gadcu::fail(GADCU_ERR_CUDA, std::string("auto replay: the recorded segment was invalidated (") + cudaGetErrorString(err) +
+                                    "); the work issued since the last flush is lost");
+  }
+  size_t nodes = 0;
+  cudaGraphGetNodes(graph, nullptr, &nodes);
+  if (nodes == 0) {
+    cudaGraphDestroy(graph);
+    return;
+  }
+  replay_segments++;
+  cudaGraphExec_t exec = nullptr;
+  auto range = replay_execs.equal_range(nodes);
+  for (auto it = range.first; it != range.second; ++it) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(it->second, graph, &info) == cudaSuccess) {  // same kernels in the same order: only parameters change
+      exec = it->second;
+      replay_hits++;
+      break;
+    }
+    cudaGetLastError();
+  }
+  if (!exec) {
+    if (replay_execs.size() >= 64) {  // a program that keeps inventing step shapes: start over
+      for (auto& kv : replay_execs) cudaGraphExecDestroy(kv.second);
+      replay_execs.clear();
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    if (ie != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      gadcu::fail(GADCU_ERR_CUDA, std::string("auto replay: cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+    }
+    replay_execs.emplace(nodes, exec);
+    replay_misses++;
+  }
+  const cudaError_t le = cudaGraphLaunch(exec, stream);
+  cudaGraphDestroy(graph);
+  if (le != cudaSuccess) gadcu::fail(GADCU_ERR_CUDA, std::string("auto replay: cudaGraphLaunch: ") + cudaGetErrorString(le));
+}
+
+namespace gadcu {
+
 std::recursive_mutex& api_mutex() {
   static std::recursive_mutex m;
   return m;
@@ -174,6 +234,9 @@ gadcu_status gadcu_ctx_destroy(gadcu_ctx* ctx) {
   return guard([&] {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    try { ctx->segment_flush(); } catch (...) {}
+    for (auto& kv : ctx->replay_execs) cudaGraphExecDestroy(kv.second);
+    ctx->replay_execs.clear();
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side_stream);
     if (ctx->pinned_scratch) cudaFreeHost(ctx->pinned_scratch);
@@ -186,9 +249,30 @@ gadcu_status gadcu_ctx_destroy(gadcu_ctx* ctx) {
 }
 
 gadcu_status gadcu_ctx_synchronize(gadcu_ctx* ctx) {
-  return guard([&] { GADCU_CUDA(cudaStreamSynchronize(ctx->stream)); });
+  return guard([&] {
+    ctx->segment_flush();
+    GADCU_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
 }
-void* gadcu_ctx_stream(gadcu_ctx* ctx) { return ctx->stream; }
+void* gadcu_ctx_stream(gadcu_ctx* ctx) {
+  guard([&] { ctx->segment_flush(); });  // whoever takes the raw stream sees everything issued so far on it
+  return ctx->stream;
+}
+gadcu_status gadcu_ctx_set_auto_replay(gadcu_ctx* ctx, int enable) {
+  return guard([&] {
+    ctx->segment_flush();
+    ctx->auto_replay = enable != 0;
+  });
+}
+gadcu_status gadcu_ctx_flush(gadcu_ctx* ctx) {
+  return guard([&] { ctx->segment_flush(); });
+}
+gadcu_status gadcu_ctx_replay_stats(gadcu_ctx* ctx, uint64_t* segments, uint64_t* reused, uint64_t* instantiated) {
+  if (segments) *segments = ctx->replay_segments;
+  if (reused) *reused = ctx->replay_hits;
+  if (instantiated) *instantiated = ctx->replay_misses;
+  return GADCU_OK;
+}
 gadcu_status gadcu_ctx_set_fusion(gadcu_ctx* ctx, int fuse) {
   ctx->fuse = fuse != 0;
   return GADCU_OK;
@@ -216,6 +300,7 @@ gadcu_status gadcu_ctx_memory_stats(gadcu_ctx* ctx, uint64_t* in_use, uint64_t* 
 
 gadcu_status gadcu_ctx_profile_begin(gadcu_ctx* ctx) {
   return guard([&] {
+    ctx->segment_flush();  // (per-kernel event timing and recorded segments exclude each other: profiled stretches run eagerly)
     for (auto& v : ctx->prof_events) {
       for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
       v.clear();
@@ -249,6 +334,7 @@ gadcu_status gadcu_array_alloc(gadcu_ctx* ctx, gadcu_dtype dt, const gadcu_dim4*
 gadcu_status gadcu_array_from_host(gadcu_ctx* ctx, gadcu_dtype dt, const gadcu_dim4* dims, const void* host, gadcu_array** out) {
   return guard([&] {
     ArrayRef a = new_array(ctx, dt, Dim4(*dims));
+    ctx->segment_flush();
     GADCU_CUDA(cudaMemcpyAsync(a->ptr(), host, a->buf->bytes, cudaMemcpyHostToDevice, ctx->stream));
     GADCU_CUDA(cudaStreamSynchronize(ctx->stream));  // `host` may be pageable and reused by the caller
     *out = a.detach();
@@ -259,6 +345,7 @@ gadcu_status gadcu_array_upload(gadcu_array* a, const void* pinned_host, void* s
     if (a->lazy()) fail(GADCU_ERR_INVALID, "upload into a lazy view");
     cudaStream_t s = stream_or_null ? static_cast<cudaStream_t>(stream_or_null) : a->ctx->stream;
     lazy_before_write(a->ctx, a->ptr());
+    a->ctx->segment_flush();
     a->buf->mutated();
     GADCU_CUDA(cudaMemcpyAsync(a->ptr(), pinned_host, a->elements() * a->elem_size(), cudaMemcpyHostToDevice, s));
   });
@@ -268,6 +355,7 @@ gadcu_status gadcu_array_upload_async(gadcu_array* a, const void* pinned_host) {
     if (a->lazy()) fail(GADCU_ERR_INVALID, "upload into a lazy view");
     gadcu_ctx* ctx = a->ctx;
     lazy_before_write(ctx, a->ptr());
+    ctx->segment_flush();
     cudaEvent_t ev;
     GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     GADCU_CUDA(cudaEventRecord(ev, ctx->stream));
@@ -279,6 +367,7 @@ gadcu_status gadcu_array_upload_async(gadcu_array* a, const void* pinned_host) {
 }
 gadcu_status gadcu_ctx_wait_uploads(gadcu_ctx* ctx) {
   return guard([&] {
+    ctx->segment_flush();
     cudaEvent_t ev;
     GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     GADCU_CUDA(cudaEventRecord(ev, ctx->side_stream));
@@ -289,6 +378,7 @@ gadcu_status gadcu_ctx_wait_uploads(gadcu_ctx* ctx) {
 gadcu_status gadcu_array_to_host(const gadcu_array* a, void* host) {
   return guard([&] {
     ArrayRef dense = materialize(ArrayRef(const_cast<gadcu_array*>(a), true));
+    a->ctx->segment_flush();
     GADCU_CUDA(cudaMemcpyAsync(host, dense->ptr(), dense->elements() * dense->elem_size(), cudaMemcpyDeviceToHost, a->ctx->stream));
     GADCU_CUDA(cudaStreamSynchronize(a->ctx->stream));
   });
@@ -319,6 +409,7 @@ gadcu_status gadcu_scalar_to_host(const gadcu_array* a, double* out) {
   return guard([&] {
     if (a->symbolic() || a->phys.elements() != 1) fail(GADCU_ERR_INVALID, "scalar_to_host on a non-scalar");
     gadcu_ctx* ctx = a->ctx;
+    ctx->segment_flush();
     std::lock_guard<std::mutex> lk(ctx->mu);
     GADCU_CUDA(cudaMemcpyAsync(ctx->pinned_scratch, a->ptr(), a->elem_size(), cudaMemcpyDeviceToHost, ctx->stream));
     GADCU_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -333,6 +424,7 @@ gadcu_status gadcu_array_random(gadcu_ctx* ctx, gadcu_dtype dt, const gadcu_dim4
                                 gadcu_array** out) {
   return guard([&] {
     ArrayRef arr = new_array(ctx, dt, Dim4(*dims));
+    ctx->segment_begin();
     k::launch_random(ctx, dt, arr->ptr(), arr->elements(), seed, normal != 0, a, b);
     *out = arr.detach();
   });
@@ -387,6 +479,7 @@ gadcu_status gadcu_array_scale(const gadcu_array* a, double lambda, gadcu_array*
 gadcu_status gadcu_capture_begin(gadcu_ctx* ctx) {
   return guard([&] {
     if (ctx->capturing) fail(GADCU_ERR_INVALID, "capture already active");
+    ctx->segment_flush();
     ctx->capture_pool = std::make_shared<Pool>();
     ctx->capturing = true;
     cudaError_t err = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed);

@@ -258,6 +258,22 @@ GADCU_API gadcu_status gadcu_store_get(const gadcu_store* s, uint32_t arena, uin
 GADCU_API size_t gadcu_store_ids(const gadcu_store* s, uint32_t* out_indices, size_t cap);
 GADCU_API gadcu_status gadcu_store_destroy(gadcu_store* s);
 
+/* ---- automatic CUDA-graph replay keyed by tape structure ------------------------------------------
+ * gad rebuilds its tape every step (net_ext.rs:52), so a captured graph has no tape to live on; but the kernels a step
+ * issues are the same sequence every time. With auto replay on, what is issued on the context's stream is recorded
+ * instead of launched, and runs as ONE graph launch at the next point where the host needs results or order: a read, a
+ * synchronise, an upload, a collective, the end of a reverse sweep (gadcu_evaluate_gradients / gadcu_compute_gradients),
+ * gadcu_ctx_flush. The recorded sequence is laid over an executable graph of the same shape kept from an earlier step
+ * (same kernels in the same order; pointers and scalars are updated), or instantiated when there is none: the structural
+ * key is the sequence itself and nothing is assumed about the program. Results are identical to eager issue. Off by
+ * default: while it is on, work issued through this API reaches gadcu_ctx_stream() only at those points (taking the
+ * stream with gadcu_ctx_stream flushes). Profiled stretches (gadcu_ctx_profile_begin) and data-parallel sweeps are
+ * issued eagerly. */
+GADCU_API gadcu_status gadcu_ctx_set_auto_replay(gadcu_ctx* ctx, int enable);
+GADCU_API gadcu_status gadcu_ctx_flush(gadcu_ctx* ctx);
+/* segments run so far; how many reused an earlier executable graph; how many had to instantiate one */
+GADCU_API gadcu_status gadcu_ctx_replay_stats(gadcu_ctx* ctx, uint64_t* segments, uint64_t* reused, uint64_t* instantiated);
+
 /* ---- CUDA-graph capture of a whole step (forward + sweep + update) -------------------------------
  * Between begin and end every launch of the ctx is recorded instead of executed; buffers allocated
  * meanwhile stay reserved for the capture, so handles created inside remain valid and are refilled

@@ -89,6 +89,8 @@ class Context {
   void set_fusion(bool fuse) { check(gadcu_ctx_set_fusion(h_, fuse)); }
   void set_lazy(bool enable, uint64_t min_elements = 32768) { check(gadcu_ctx_set_lazy(h_, enable, min_elements)); }
   void set_gemm_epilogue(bool enable) { check(gadcu_ctx_set_gemm_epilogue(h_, enable)); }
+  void set_auto_replay(bool enable) { check(gadcu_ctx_set_auto_replay(h_, enable)); }  // graphs keyed by the recorded kernel sequence
+  void flush() { check(gadcu_ctx_flush(h_)); }
   uint64_t launches() {
     uint64_t a, b, c;
     check(gadcu_ctx_memory_stats(h_, &a, &b, &c));

@@ -152,6 +152,9 @@ extern "C" {
     pub fn gadcu_ctx_set_lazy(ctx: *mut gadcu_ctx, enable: c_int, min_elements: u64) -> gadcu_status;
     pub fn gadcu_ctx_set_strict_reference(ctx: *mut gadcu_ctx, strict: c_int) -> gadcu_status;
     pub fn gadcu_ctx_set_gemm_epilogue(ctx: *mut gadcu_ctx, enable: c_int) -> gadcu_status;
+    pub fn gadcu_ctx_set_auto_replay(ctx: *mut gadcu_ctx, enable: c_int) -> gadcu_status;
+    pub fn gadcu_ctx_flush(ctx: *mut gadcu_ctx) -> gadcu_status;
+    pub fn gadcu_ctx_replay_stats(ctx: *mut gadcu_ctx, segments: *mut u64, reused: *mut u64, instantiated: *mut u64) -> gadcu_status;
     pub fn gadcu_ctx_memory_stats(ctx: *mut gadcu_ctx, bytes_in_use: *mut u64, bytes_reserved: *mut u64, kernel_launches: *mut u64) -> gadcu_status;
     pub fn gadcu_ctx_profile_begin(ctx: *mut gadcu_ctx) -> gadcu_status;
     pub fn gadcu_ctx_profile_end(ctx: *mut gadcu_ctx, ms_by_category4: *mut f64, count_by_category4: *mut u64) -> gadcu_status;
