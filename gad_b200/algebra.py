@@ -157,8 +157,9 @@ class Context:
         _check(self.lib.gadcu_ctx_replay_stats(self.handle, C.byref(a), C.byref(b), C.byref(c)))
         return {"segments": a.value, "reused": b.value, "instantiated": c.value}
 
-    def set_gemm_epilogue(self, enable: bool) -> None:
-        """Fused GEMM epilogues (gadcu_ctx_set_gemm_epilogue): on by default; off = every product launched where it is recorded."""
+    def set_gemm_epilogue(self, enable) -> None:
+        """Fused GEMM epilogues (gadcu_ctx_set_gemm_epilogue): 1 / True = where it pays (default), 2 = always, 0 / False = every
+        product launched where it is recorded."""
         _check(self.lib.gadcu_ctx_set_gemm_epilogue(self.handle, int(enable)))
 
     def set_strict_reference(self, strict: bool) -> None:

@@ -102,7 +102,7 @@ struct gadcu_ctx {
   bool capturing = false;
   bool fuse = true;
   bool strict_reference = false;  // reproduce the reference's matmul VJP for transposed operands as is
-  bool gemm_epilogue = true;      // deferred products with their elementwise tail in the GEMM's epilogue (gadcu_ctx_set_gemm_epilogue)
+  int gemm_epilogue = 1;          // deferred products with their elementwise tail in the GEMM's epilogue: 0 never, 1 where it pays, 2 always (gadcu_ctx_set_gemm_epilogue)
   std::atomic<uint64_t> launches{0};
   std::atomic<bool> comm_inflight{false};  // an overlapped collective is running: GEMMs leave it a few SMs
   std::atomic<uint64_t> epoch{1};

@@ -283,7 +283,7 @@ gadcu_status gadcu_ctx_set_lazy(gadcu_ctx* ctx, int enable, uint64_t min_element
   return GADCU_OK;
 }
 gadcu_status gadcu_ctx_set_gemm_epilogue(gadcu_ctx* ctx, int enable) {
-  ctx->gemm_epilogue = enable != 0;
+  ctx->gemm_epilogue = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   return GADCU_OK;
 }
 gadcu_status gadcu_ctx_set_strict_reference(gadcu_ctx* ctx, int strict) {
