@@ -155,6 +155,7 @@ using Algebra = ::gadcu_algebra;
 class EvalAlgebra final : public Algebra {
  public:
   explicit EvalAlgebra(gadcu_ctx* c) : Algebra(c) {}
+  bool fuse_tails = true;  // deferred products may run with their elementwise tail in the epilogue (off under a GraphN: batched.cu lazy_matmul)
   gadcu_algebra_kind kind() const override { return GADCU_EVAL; }
   gadcu_algebra* clone() const override { return new EvalAlgebra(ctx); }
   bool is_eval() const override { return true; }

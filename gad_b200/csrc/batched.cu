@@ -98,6 +98,7 @@ struct SymProgram {
     ArrayRef a, b;
     MatProp p1, p2;
     Dim4 rd;
+    bool fusable;  // false: launched plain when first needed (higher-order tapes: see lazy_matmul)
   };
   std::unordered_map<int32_t, PendingGemm> pending;
   // columns that must outlive their handles: what a deferred product left behind (its own result, or the result of the
@@ -1228,7 +1229,7 @@ void SymProgram::resolve_pending(const std::vector<int32_t>& todo) {
     int32_t result_reg = -1;
     std::vector<int32_t> inside;  // registers of the tail other than its result
     bool split = false;
-    if (fuse_on && readers.size() == 1) {
+    if (fuse_on && pg.fusable && readers.size() == 1) {
       const int32_t r1 = readers[0];
       const SymInstr& I1 = instrs[r1];
       auto other = [&](const SymInstr& I) { return I.a == g ? I.b : I.a; };
@@ -1302,7 +1303,7 @@ void SymProgram::resolve_pending(const std::vector<int32_t>& todo) {
 
 // matmul recorded instead of launched (EvalAlgebra::matmul when deferred regions are on): the product joins the region of
 // its [M, N] result as a leaf, so that the elementwise ops a layer puts behind it can ride in the GEMM's epilogue.
-ArrayRef lazy_matmul(gadcu_ctx* ctx, const ArrayRef& a, const ArrayRef& b, MatProp p1, MatProp p2, const Dim4& rd);
+ArrayRef lazy_matmul(gadcu_ctx* ctx, const ArrayRef& a, const ArrayRef& b, MatProp p1, MatProp p2, const Dim4& rd, bool fusable);
 
 // ---- the symbolic per-lane eval algebra ---------------------------------------------------------
 class SymAlgebra final : public Algebra {
@@ -1553,7 +1554,11 @@ ArrayRef lazy_elementwise(gadcu_ctx* ctx, k::EwOp op, const ArrayRef& acc, const
   return sym_array(prog, r, dims, is_scalar);
 }
 
-ArrayRef lazy_matmul(gadcu_ctx* ctx, const ArrayRef& a_in, const ArrayRef& b_in, MatProp p1, MatProp p2, const Dim4& rd) {
+// `fusable` = false on higher-order tapes (GraphN): there the values inside a tail (the product itself, product + bias) are
+// captured by recorded backward nodes and ARE read later, by the next sweep; a product that ran fused has not kept them
+// and would have to be launched a second time. Such products are still deferred (one nothing depends on is never
+// launched) but run plain.
+ArrayRef lazy_matmul(gadcu_ctx* ctx, const ArrayRef& a_in, const ArrayRef& b_in, MatProp p1, MatProp p2, const Dim4& rd, bool fusable) {
   // the program keeps the operands' BUFFERS, through handles of its own: a computed deferred value still carries the
   // handle of the program that computed it, and holding that here would tie the program to itself for good
   const ArrayRef a = view_array(a_in, a_in->dims, a_in->phys, a_in->is_scalar), b = view_array(b_in, b_in->dims, b_in->phys, b_in->is_scalar);
@@ -1565,7 +1570,7 @@ ArrayRef lazy_matmul(gadcu_ctx* ctx, const ArrayRef& a_in, const ArrayRef& b_in,
     prog->instrs.push_back(I);  // (never value-numbered: two products are two launches)
     prog->live.push_back(0);
     r = int32_t(prog->instrs.size() - 1);
-    prog->pending.emplace(r, SymProgram::PendingGemm{a, b, p1, p2, rd});
+    prog->pending.emplace(r, SymProgram::PendingGemm{a, b, p1, p2, rd, fusable});
   }
   return sym_array(prog, r, rd, false);
 }

@@ -19,7 +19,7 @@ ArrayRef lazy_elementwise(gadcu_ctx* ctx, k::EwOp op, const ArrayRef& acc, const
                           gadcu_dtype dt, const Dim4& dims, bool is_scalar);
 // a matmul recorded as a leaf of the region of its result (launched when something needs it, with the elementwise tail
 // behind it in the GEMM's epilogue where that is one of the known ones: GemmEpilogue)
-ArrayRef lazy_matmul(gadcu_ctx* ctx, const ArrayRef& a, const ArrayRef& b, MatProp p1, MatProp p2, const Dim4& rd);
+ArrayRef lazy_matmul(gadcu_ctx* ctx, const ArrayRef& a, const ArrayRef& b, MatProp p1, MatProp p2, const Dim4& rd, bool fusable);
 void lazy_before_write(gadcu_ctx* ctx, const void* buffer);
 void lazy_flush(const std::vector<ArrayRef>& values);
 

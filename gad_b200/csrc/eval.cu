@@ -455,7 +455,7 @@ ArrayRef EvalAlgebra::matmul_acc(ArrayRef acc, const ArrayRef& a_in, const Array
   const bool worth_it = ctx->gemm_epilogue == 2 || (ctx->gemm_epilogue == 1 && tiles > uint64_t(ctx->sm_count / 2));
   if (!acc && defer && worth_it && g.batch == 1 && g.dt == GADCU_F32 && lazy_enabled(ctx, rd.elements(), false) &&
       k::gemm_epilogue_supported(g))
-    return lazy_matmul(ctx, a, b, p1, p2, rd);
+    return lazy_matmul(ctx, a, b, p1, p2, rd, fuse_tails);
   ArrayRef out;
   if (acc) {
     if (acc->dims != rd) fail(GADCU_ERR_DIMENSIONS, "Incompatible dimensions for add: " + acc->dims.str() + " " + rd.str());

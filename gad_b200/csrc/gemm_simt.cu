@@ -91,6 +91,25 @@ void launch_gemm(gadcu_ctx* ctx, const GemmArgs& g) {
     launch_gemm_tc(ctx, g);
     return;
   }
+  // af::matmul over batch dims 2, 3 with broadcast (gad/src/matrix.rs:108-114): when one matrix of the batch is a product
+  // the tensor-core kernel takes, the batch is that kernel once per matrix (a broadcast operand — stride 0 — keeps its
+  // TF32 split across the launches through the buffer's cache)
+  if (g.batch > 1 && !g.push && !g.epi && g.batch <= 4096) {
+    GemmArgs one = g;
+    one.batch = 1;
+    if (gemm_tc_supported(one)) {
+      const size_t es = 4;
+      for (uint64_t b = 0; b < g.batch; b++) {
+        one.A = static_cast<const char*>(g.A) + b * g.strideA * es;
+        one.B = static_cast<const char*>(g.B) + b * g.strideB * es;
+        one.C = static_cast<char*>(g.C) + b * g.strideC * es;
+        one.a_buf = g.strideA == 0 ? g.a_buf : nullptr;  // (a slice of a batched operand is not a whole buffer)
+        one.b_buf = g.strideB == 0 ? g.b_buf : nullptr;
+        launch_gemm_tc(ctx, one);
+      }
+      return;
+    }
+  }
   if (g.push) fail(GADCU_ERR_UNSUPPORTED, "gemm: the tile-pushing epilogue exists on the f32 tensor-core path only");
   if (gemm_dmma_supported(g)) {
     launch_gemm_dmma(ctx, g);

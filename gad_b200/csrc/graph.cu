@@ -43,6 +43,8 @@ static std::atomic<uint32_t> g_arena_counter{1};
 GraphAlgebra::GraphAlgebra(gadcu_ctx* c, bool higher_order, std::shared_ptr<Algebra> eval)
     : Algebra(c), higher_order_(higher_order), arena_id_(g_arena_counter.fetch_add(1)),
       eval_(eval ? std::move(eval) : std::make_shared<EvalAlgebra>(c)) {
+  if (higher_order)
+    if (auto* ev = dynamic_cast<EvalAlgebra*>(eval_.get())) ev->fuse_tails = false;
   c->epoch.fetch_add(1, std::memory_order_relaxed);  // a new tape: TF32 splits cached by earlier steps expire
 }
 

@@ -108,3 +108,26 @@ def test_gemm_tc_ragged_mlp_gradients(ctx):
         got = to_np(got)[:, :, 0, 0].astype(np.float64)
         assert got.shape == want.shape
         assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("ad,bd", [((256, 128, 3), (128, 256)), ((256, 128), (128, 256, 2, 2)), ((300, 200, 2), (200, 260, 2))])
+def test_batched_matmul_takes_the_tensor_core_path(ctx, ad, bd):
+    """af::matmul over batch dims 2, 3 with broadcast (gad/src/matrix.rs:108-114): one tensor-core launch per matrix of the
+    batch, against f64 numpy under the 3xTF32 bound."""
+    rng = np.random.default_rng(17)
+    a, b = rng.standard_normal(ad).astype(np.float32), rng.standard_normal(bd).astype(np.float32)
+    ev = gb.Eval(ctx)
+    ctx.profile_begin()
+    got = to_np(ev.matmul(ev.constant(a), ev.constant(b)))
+    prof = ctx.profile_end()
+    a4, b4 = a.reshape(ad + (1,) * (4 - len(ad))), b.reshape(bd + (1,) * (4 - len(bd)))
+    batch = (max(a4.shape[2], b4.shape[2]), max(a4.shape[3], b4.shape[3]))
+    assert got.shape == (ad[0], bd[1]) + batch
+    K = ad[1]
+    for i in range(batch[0]):
+        for j in range(batch[1]):
+            A = a4[:, :, i % a4.shape[2], j % a4.shape[3]].astype(np.float64)
+            B = b4[:, :, i % b4.shape[2], j % b4.shape[3]].astype(np.float64)
+            bound = (2.0 ** -20 + 3 * (K / 8) * 2.0 ** -23) * (np.abs(A) @ np.abs(B))
+            assert np.all(np.abs(got[:, :, i, j].astype(np.float64) - A @ B) <= bound), (i, j)
+    assert prof["matmul"]["launches"] == 1  # one dispatch ...
