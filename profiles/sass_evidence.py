@@ -8,7 +8,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "gad_b200", "lib", "libgadcu.so")
-MNEMONICS = r"\b(UTC[A-Z]*MMA|UTCBAR|UTCATOMSWS|LDTM|STTM|UTMALDG|UTMASTG|UBLKCP|HMMA|DMMA|SYNCS|ATOMG|REDG|RED|MEMBAR|LDG|STG|LDS|STS|SHFL|MUFU)\b"
+MNEMONICS = r"\b(LDGMC|UTC[A-Z]*MMA|UTCBAR|UTCATOMSWS|LDTM|STTM|UTMALDG|UTMASTG|UBLKCP|HMMA|DMMA|SYNCS|ATOMG|REDG|RED|MEMBAR|LDG|STG|LDS|STS|SHFL|MUFU)\b"
 
 
 def demangle(name):
