@@ -40,14 +40,15 @@ def main():
     print("cuobjdump -sass / --dump-resource-usage gad_b200/lib/libgadcu.so (sm_100a), one entry per kernel; static instruction counts")
     print("tensor-core path: UTCHMMA = tcgen05.mma (kind::tf32), UTCBAR = tcgen05.commit, UTCATOMSWS = TMEM alloc/dealloc, LDTM = tcgen05.ld,")
     print("UTMALDG = cp.async.bulk.tensor (TMA), SYNCS = mbarrier ops, DMMA = mma.sync f64. In gemm_tf32x3_pair_kernel the STG group includes the")
-    print("tile-pushing epilogue's stores to peer (NVLink-mapped) staging buffers, in the same kernel as the UTCHMMA tiles.\n")
+    print("tile-pushing epilogue's stores to peer (NVLink-mapped) staging buffers, in the same kernel as the UTCHMMA tiles.")
+    print("LDGMC.E.ADD.F32x4 = multimem.ld_reduce.add.v4.f32 (the NVSwitch reduces the address over all ranks); multimem.st is an STG.E.128.STRONG.SYS on the multicast address.\n")
     for fn in sorted(counts, key=lambda f: (-sum(v for k, v in counts[f].items() if k.startswith("UTC") or k in ("DMMA", "LDTM", "UTMALDG")), f)):
         name = demangle(fn)
-        if "gadcu" not in name:
-            continue
+        if "gadcu" not in name and not name.startswith(("dp_", "void dp_")) and "dp_nvls" not in name:
+            continue  # (the exchange kernels of comm.cu sit in an anonymous namespace inside extern "C": no gadcu:: in their names)
         reg, sh, loc = usage.get(fn, (None, None, None))
         c = counts[fn]
-        keys = [k for k in ("UTCHMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "UTMALDG", "UBLKCP", "SYNCS", "DMMA", "HMMA", "LDG", "STG", "ATOMG", "RED", "REDG", "MEMBAR", "SHFL", "MUFU") if c.get(k)]
+        keys = [k for k in ("LDGMC", "UTCHMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "UTMALDG", "UBLKCP", "SYNCS", "DMMA", "HMMA", "LDG", "STG", "ATOMG", "RED", "REDG", "MEMBAR", "SHFL", "MUFU") if c.get(k)]
         print(f"{name[:150]}\n    registers {reg}, static shared {sh} B, local (spills) {loc} B;  " + ", ".join(f"{k} x{c[k]}" for k in keys))
 
 
