@@ -695,14 +695,93 @@ std::string gen_source(const SymProgram& P, const JitPlan& J, const std::unorder
   }
   for (size_t k = 0; k < NO; k++) o << "  o" << k << " = " << reg_name(J.outs[k]) << ";\n";
   o << "}\n";
-  // ---- kernel skeleton: all loads of U vectors first, then compute + store
-  const char* lanes4[] = {".x", ".y", ".z", ".w"};
-  o << "extern \"C\" __global__ void __launch_bounds__(" << J.block << ") lane_program(const P p) {\n";
-  o << "  const u64 tid = (u64)blockIdx.x * " << J.block << "ull + threadIdx.x;\n  const u64 stride = (u64)gridDim.x * " << J.block << "ull;\n";
-  for (auto& d : J.uniform) o << "  const T " << reg_name(d.first) << " = p.in[" << d.second << "][0];\n";
   auto col_index = [&](size_t k, const std::string& i) {
     return J.idx32 ? "(unsigned)(" + i + ") / (unsigned)p.td[" + std::to_string(k) + "]" : "(" + i + ") / p.td[" + std::to_string(k) + "]";
   };
+  const char* lanes4[] = {".x", ".y", ".z", ".w"};
+  if (J.ring) {
+    // ---- ring-fed skeleton (array mode, large regions): a producer warp streams the dense inputs, tile by tile
+    // (BLOCK vectors of 16 bytes per input = 8 KB bulk copies), through a shared-memory ring with cp.async.bulk +
+    // full / empty mbarriers and runs ahead across tiles; the BLOCK computing threads take one vector per input and tile
+    // from the ring. Bytes in flight then cost no registers and do not depend on what the computing warps are doing
+    // (the register-fed shape alternates between waiting for its loads and ~1000 instructions of exp / log / div:
+    // measured on the C3 sweep, 64 Mi f32: 0.191 ms register-fed, 0.177 ms ring-fed, same bits; smaller tiles or
+    // deeper rings are slower — experiments/c3_sweep_ring.cu).
+    const int D = J.ring, B = J.block, ND = int(J.dense.size());
+    int logd = 0;
+    while ((1 << logd) < D) logd++;
+    o << "#define TILE_BYTES " << B * 16 << "u\n";
+    o << "__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {\n  unsigned done;\n  do {\n"
+         "    asm volatile(\"{\\n.reg .pred p;\\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\\nselp.u32 %0, 1, 0, p;\\n}\" : \"=r\"(done) : \"r\"(bar), \"r\"(parity) : \"memory\");\n"
+         "  } while (!done);\n}\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(" << B + 32 << ", " << J.stage_blocks << ") lane_program(const P p) {\n";
+    o << "  extern __shared__ __align__(128) unsigned char smem[];\n";
+    o << "  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem), bfull = sbase + " << D << "u * TILE_BYTES, bempty = bfull + " << 8 * D << "u;\n";
+    o << "  if (threadIdx.x == 0) {\n    for (unsigned s = 0; s < " << D << "u; s++) {\n"
+         "      asm volatile(\"mbarrier.init.shared::cta.b64 [%0], %1;\" ::\"r\"(bfull + 8 * s), \"r\"(1u));\n"
+         "      asm volatile(\"mbarrier.init.shared::cta.b64 [%0], %1;\" ::\"r\"(bempty + 8 * s), \"r\"(" << B / 32 << "u));\n    }\n"
+         "    asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n"
+         "    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n  }\n  __syncthreads();\n";
+    o << "  const u64 nvec = p.n / " << J.V << ";\n  const u64 tiles = (nvec + " << B - 1 << "ull) / " << B << "ull;\n";
+    // producer
+    o << "  if (threadIdx.x >= " << B << ") {\n    if (threadIdx.x == " << B << ") {\n      unsigned q = 0;\n"
+         "      for (u64 t = blockIdx.x; t < tiles; t += gridDim.x) {\n"
+         "        const u64 first = t * " << B << "ull;\n        const u64 left = nvec - first;\n"
+         "        const unsigned bytes = (unsigned)(left < " << B << "ull ? left : " << B << "ull) * 16u;\n";
+    for (int j = 0; j < ND; j++) {
+      o << "        {\n          const unsigned s = q & " << D - 1 << "u, ph = (q >> " << logd << ") & 1u;\n"
+           "          mbar_wait(bempty + 8 * s, ph ^ 1u);\n"
+           "          asm volatile(\"mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\" ::\"r\"(bfull + 8 * s), \"r\"(bytes) : \"memory\");\n"
+           "          asm volatile(\"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\" ::\"r\"(sbase + s * TILE_BYTES), "
+           "\"l\"(reinterpret_cast<const TV*>(p.in[" << J.dense[size_t(j)].second << "]) + first), \"r\"(bytes), \"r\"(bfull + 8 * s) : \"memory\");\n"
+           "          q++;\n        }\n";
+    }
+    o << "      }\n    }\n    return;\n  }\n";
+    // consumers
+    for (auto& d : J.uniform) o << "  const T " << reg_name(d.first) << " = p.in[" << d.second << "][0];\n";
+    o << "  unsigned q = 0;\n  for (u64 t = blockIdx.x; t < tiles; t += gridDim.x) {\n    const u64 vi = t * " << B << "ull + threadIdx.x;\n";
+    for (int j = 0; j < ND; j++) {
+      o << "    TV v" << J.local.at(J.dense[size_t(j)].first) << ";\n    {\n      const unsigned s = q & " << D - 1 << "u;\n"
+           "      mbar_wait(bfull + 8 * s, (q >> " << logd << ") & 1u);\n"
+           "      v" << J.local.at(J.dense[size_t(j)].first) << " = *reinterpret_cast<const TV*>(smem + s * TILE_BYTES + threadIdx.x * 16u);\n"
+           "      __syncwarp();\n"
+           "      if ((threadIdx.x & 31) == 0) asm volatile(\"mbarrier.arrive.shared::cta.b64 _, [%0];\" ::\"r\"(bempty + 8 * s) : \"memory\");\n"
+           "      q++;\n    }\n";
+    }
+    o << "    if (vi < nvec) {\n";
+    for (size_t k = 0; k < J.col.size(); k++)
+      o << "      const T " << reg_name(J.col[k].first) << " = p.in[" << J.col[k].second << "][" << col_index(k, "vi * " + std::to_string(J.V)) << "];\n";
+    for (size_t k = 0; k < NO; k++) o << "      TV y" << k << ";\n";
+    for (int l = 0; l < J.V; l++) {
+      o << "      body(p, vi * " << J.V << " + " << l;
+      for (auto& d : J.dense) o << ", v" << J.local.at(d.first) << lanes4[l];
+      for (auto& d : J.uniform) o << ", " << reg_name(d.first);
+      for (auto& d : J.col) o << ", " << reg_name(d.first);
+      for (size_t k = 0; k < NO; k++) o << ", y" << k << lanes4[l];
+      o << ");\n";
+    }
+    for (size_t k = 0; k < NO; k++) o << "      reinterpret_cast<TV*>(p.out[" << k << "])[vi] = y" << k << ";\n";
+    o << "    }\n  }\n";
+    // scalar tail (n not a multiple of the vector width): the computing threads of all blocks share it
+    o << "  for (u64 i = nvec * " << J.V << " + (u64)blockIdx.x * " << B << "ull + threadIdx.x; i < p.n; i += (u64)gridDim.x * " << B << "ull) {\n";
+    for (auto& d : J.dense) o << "    const T s" << J.local.at(d.first) << " = __ldcs(p.in[" << d.second << "] + i);\n";
+    for (size_t k = 0; k < J.col.size(); k++)
+      o << "    const T " << reg_name(J.col[k].first) << " = p.in[" << J.col[k].second << "][" << col_index(k, "i") << "];\n";
+    for (size_t k = 0; k < NO; k++) o << "    T y" << k << ";\n";
+    o << "    body(p, i";
+    for (auto& d : J.dense) o << ", s" << J.local.at(d.first);
+    for (auto& d : J.uniform) o << ", " << reg_name(d.first);
+    for (auto& d : J.col) o << ", " << reg_name(d.first);
+    for (size_t k = 0; k < NO; k++) o << ", y" << k;
+    o << ");\n";
+    for (size_t k = 0; k < NO; k++) o << "    p.out[" << k << "][i] = y" << k << ";\n";
+    o << "  }\n}\n";
+    return o.str();
+  }
+  // ---- kernel skeleton: all loads of U vectors first, then compute + store
+  o << "extern \"C\" __global__ void __launch_bounds__(" << J.block << ") lane_program(const P p) {\n";
+  o << "  const u64 tid = (u64)blockIdx.x * " << J.block << "ull + threadIdx.x;\n  const u64 stride = (u64)gridDim.x * " << J.block << "ull;\n";
+  for (auto& d : J.uniform) o << "  const T " << reg_name(d.first) << " = p.in[" << d.second << "][0];\n";
   if (J.V > 1) {
     o << "  const u64 nvec = p.n / " << J.V << ";\n";
     o << "  for (u64 base = tid; base < nvec; base += stride * " << J.U << ") {\n";
@@ -891,6 +970,19 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   J.U = J.V == 1 ? 1 : (streams <= 4 && J.order.size() <= 64 ? 4 : (streams <= 8 && J.order.size() <= 128 ? 2 : 1));
   J.block = J.order.size() > 256 ? 128 : 256;
   J.idx32 = lanes < (1ull << 32);
+  if (array_mode && J.V == vmax && J.order.size() <= 256 && !J.dense.empty() && J.dense.size() <= 4 && lanes >= (1ull << 22)) {
+    // large region: feed the dense inputs through a shared-memory ring (see gen_source). 512-thread tiles, ring of 4
+    // (8 with more than two inputs: two tiles' worth in flight), two blocks per SM if the registers allow.
+    static const int region_ring = [] { const char* e = getenv("GADCU_REGION_RING"); return e ? atoi(e) : 1; }();
+    bool aligned = true;
+    for (auto& d : J.dense) aligned = aligned && (reinterpret_cast<uintptr_t>(J.in_ptrs[size_t(d.second)]) & 15) == 0;
+    if (region_ring && aligned) {
+      J.ring = J.dense.size() <= 2 ? 4 : 8;
+      J.block = 512;
+      J.U = 1;
+      J.smem_bytes = size_t(J.ring) * 512 * 16 + size_t(J.ring) * 16;
+    }
+  }
   if (J.V == 1 && J.order.size() > 256) {
     // greedy list scheduling for few live values: among the ready instructions take the one that ends the most
     // live ranges (net of the one it starts); prefer computing over loading, then tape order
@@ -1076,7 +1168,8 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
       auto it = chosen.find(key);
       if (it != chosen.end()) known = it->second;
     }
-    const std::vector<int> candidates = known ? std::vector<int>{known} : forced > 0 ? std::vector<int>{forced} : std::vector<int>{5, 3, 2};
+    const std::vector<int> candidates = known ? std::vector<int>{known} : (forced > 0 && J.flat) ? std::vector<int>{forced}
+                                              : J.flat ? std::vector<int>{5, 3, 2} : std::vector<int>{2, 1};  // (array mode: 544-thread blocks, <= 56 registers for two per SM)
     for (size_t c = 0; c < candidates.size(); c++) {
       J.stage_blocks = candidates[c];
       kernel = build(key + "|b" + std::to_string(J.stage_blocks));

@@ -912,7 +912,8 @@ PairPlan plan_pair(int sm_count, bool comm_inflight, uint64_t M, uint64_t N, uin
     // ... and not for a single partial wave that already covers most of the chip (64 tiles on 74 clusters, the 1024-row
     // shards of an 8-GPU step): no gain alone (0.132 ms either way: the idle SMs' power goes to the busy ones) and 2.5 %
     // slower inside the 8-GPU step (516 vs 503 steps/s), where the idle SMs are what the exchange kernels run on
-    const bool lone_wide_wave = tiles < p.clusters && tiles * 2 > p.clusters;
+    static const bool lone_ok = [] { const char* e = getenv("GADCU_GEMM_SK_LONE"); return e && atoi(e) != 0; }();  // (A/B switch)
+    const bool lone_wide_wave = !lone_ok && tiles < p.clusters && tiles * 2 > p.clusters;
     if (tail >= min_tail && gain >= 0.03 && !lone_wide_wave) p.rem = uint32_t(rem), p.tail_kb = uint32_t(tail);
   }
   p.splits = push_splits ? uint32_t(push_splits) : ((streamk || no_split) ? 1u : choose_splits_for(sm_count, M, N, K, accumulate, bkt));  // (push: the exchange laid its staging out for this)

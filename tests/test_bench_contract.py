@@ -97,3 +97,46 @@ def test_committed_bench_lines_carry_the_whole_contract():
                 assert key in sec, key
             assert sec["grad_sweep"]["roofline"]["bound"] == "hbm" and sec["batched_tape"]["roofline"]["bound"] == "hbm"
             assert sec["grad_sweep"]["cpu_baseline"]["kind"] == "port" and sec["batched_tape"]["cpu_baseline"]["cores"] >= 1
+
+
+def test_committed_round2_bench_lines_carry_parity_dp_check_and_the_secondary_rows():
+    """profiles/r02_bench_n{1,2,4,8}.json: what VERDICT r01 asked of every line — one fixed roofline denominator with the
+    source of `traffic`, a parity object per row, `dp_check` in every N > 1 line, C2 and C5 over the ranks."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench_n[1248].json")))
+    assert len(files) == 4
+    for path in files:
+        line = _json_lines(open(path).read())[-1]
+        n = line["n_gpus"]
+        assert os.path.basename(path) == f"r02_bench_n{n}.json"
+        for k in ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                  "config", "clocks", "e2e", "gpu_launches", "roofline"]:
+            assert k in line, (path, k)
+        assert line["metric"] == "MLP fwd+bwd steps/s" and line["scaling"] == "strong" and line["vs_baseline"] is None and line["warmup"] >= 3
+        r = line["roofline"]
+        assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and "burst" in r["peak_source"]
+        assert "frac_of_sustained_peak" in r and "frac_of_burst_peak" not in r  # one denominator, the other a side field
+        e = line["e2e"]
+        assert e["h2d_bytes_per_step"] == 8192 * 4096 * 4 * 2 and e["d2h_bytes_per_step"] == 4 * n and 0 < e["value"] <= line["value"] * 1.02
+        assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"]))
+        sec = line["secondary"]
+        if n == 1:
+            assert r["traffic"] > 0 and "@" in r["traffic_source"] and r["traffic_source"].startswith("profiles/")
+            cb = line["cpu_baseline"]
+            assert cb["kind"] == "port" and "sgemm" in cb["gemm"] and cb["sample"].startswith("8192 of 8192")
+            assert line["parity"]["vs"] == "oracle" and 0 < line["parity"]["max_rel"] < 1e-3
+            for key in ["grad_sweep", "batched_tape", "hvp", "graph_replay", "scalar_tape"]:
+                assert key in sec, key
+            assert sec["grad_sweep"]["parity"]["vs"] == "oracle" and sec["batched_tape"]["parity"]["bit_identical"] is True
+            h = sec["hvp"]
+            assert h["roofline"]["bound"] == "tensor" and h["cpu_baseline"]["kind"] == "port" and h["parity"]["max_rel"] < 1e-3
+            bt = sec["batched_tape"]
+            assert bt["compiled_host"]["same_bits_as_python_recorded"] is True and bt["compiled_host"]["ms_per_call"] < 1.0
+            gr = sec["graph_replay"]["mlp_small"]
+            assert gr["auto_loss_identical"] is True and gr["auto_replay_segments"]["instantiated"] == 0
+        else:
+            dc = line["dp_check"]
+            assert dc["rows_per_gpu"] == 8192 // n and dc["fused_repeatable"] is True
+            assert dc["fused_vs_nccl_max_rel"] < 1e-4 and dc["vs_full_batch_on_one_gpu"]["max_rel"] < 1e-4
+            assert sec["hvp"]["n_gpus"] == n and sec["hvp"]["value"] > 0
+            assert sec["batched_tape"]["n_gpus"] == n and sec["batched_tape"]["lanes_per_gpu"] == (1 << 20) // n

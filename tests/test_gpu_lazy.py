@@ -150,3 +150,31 @@ def test_graphn_records_through_deferred_regions(lazy_ctx, oracle):
     a, b = hess(True), hess(False)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert np.allclose(a[0], 2 * x, rtol=1e-6) and np.allclose(a[1], 2 * y, rtol=1e-6)
+
+
+@pytest.mark.parametrize("n_rows,n_cols", [((1 << 22) + 3, 1), (4099, 1031), (8192, 1024)])
+def test_large_regions_take_the_ring_fed_kernel_and_keep_their_bits(ctx, n_rows, n_cols):
+    """Regions of >= 2^22 elements stream their dense inputs through a shared-memory ring (cp.async.bulk producer warp):
+    same values as the eager one-kernel-per-op path, for a length that is not a multiple of the vector width, with a
+    column-tiled operand, several dense inputs and two outputs."""
+    rng = np.random.default_rng(21)
+    shape = (n_rows, n_cols) if n_cols > 1 else (n_rows,)
+    x = rng.uniform(-1, 1, shape).astype(np.float32)
+    y = rng.uniform(0.5, 2, shape).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+    b = rng.uniform(-1, 1, (1, n_cols)).astype(np.float32)
+
+    def run(lazy):
+        ctx.set_lazy(lazy)
+        try:
+            ev = gb.Eval(ctx)
+            vx, vy, vw = ev.constant(x), ev.constant(y), ev.constant(w)
+            t = ev.tanh(ev.add(vx, ev.tile_as(ev.constant(b), shape))) if n_cols > 1 else ev.tanh(vx)
+            u = ev.mul(ev.exp(t), ev.log(vy))
+            v = ev.div(ev.add(u, vw), vy)
+            return to_np(u), to_np(v)
+        finally:
+            ctx.set_lazy(True)
+
+    a, e = run(True), run(False)
+    assert np.array_equal(a[0], e[0]) and np.array_equal(a[1], e[1])
