@@ -446,13 +446,15 @@ ArrayRef EvalAlgebra::matmul_acc(ArrayRef acc, const ArrayRef& a_in, const Array
   // A product nothing is accumulated into, whose [M, N] result would be deferred elementwise territory anyway, is recorded
   // rather than launched: what the layer does next to it (+ bias, tanh; the tanh VJP on an incoming dA; the residual of
   // the square loss) then runs in the GEMM's epilogue (batched.cu: lazy_matmul / resolve_pending).
-  // Worth it when the product has more output tiles than the chip has SM pairs: the tail of tile i then runs while the
-  // tensor cores work on tile i + 1 (double-buffered accumulators). With a single wave of tiles the tail would sit on the
-  // critical path of a few SMs while the rest of the chip idles — there the separate, chip-wide elementwise kernel is the
-  // faster way (measured: a 512 x 256 step 0.31 ms unfused, 0.39 fused; 1024-row shards of the 8-GPU step: no difference).
+  // Worth it when the product's output tiles keep at least half of the chip's SM pairs busy. With several waves of tiles
+  // the tail of tile i runs while the tensor cores work on tile i + 1 (double-buffered accumulators); with one well-filled
+  // wave it adds a few microseconds to the launch but saves the separate elementwise and split kernels (measured inside
+  // one call, 8 GPUs, 64-tile products of the 1024-row shards: 636.6 steps/s fused, 592.1 not). With a handful of tiles it
+  // would sit on the critical path of a few SMs while the rest of the chip idles — there the chip-wide elementwise kernel
+  // is faster (a 512 x 256 step, 2 tiles per product: 0.31 ms unfused, 0.39 fused).
   // gadcu_ctx_set_gemm_epilogue(ctx, 2) fuses regardless (the parity tests do, at small shapes).
   const uint64_t tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256);
-  const bool worth_it = ctx->gemm_epilogue == 2 || (ctx->gemm_epilogue == 1 && tiles > uint64_t(ctx->sm_count / 2));
+  const bool worth_it = ctx->gemm_epilogue == 2 || (ctx->gemm_epilogue == 1 && tiles * 2 >= uint64_t(ctx->sm_count / 2));
   if (!acc && defer && worth_it && g.batch == 1 && g.dt == GADCU_F32 && lazy_enabled(ctx, rd.elements(), false) &&
       k::gemm_epilogue_supported(g))
     return lazy_matmul(ctx, a, b, p1, p2, rd, fuse_tails);

@@ -223,6 +223,7 @@ gadcu_status gadcu_ctx_create(int device, gadcu_ctx** out) {
     GADCU_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     ctx->pool = std::make_shared<Pool>();
+    if (const char* e = getenv("GADCU_EPILOGUE")) ctx->gemm_epilogue = atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e));  // 0 never, 1 where it pays, 2 always
     GADCU_CUDA(cudaMallocHost(&ctx->pinned_scratch, 4096));
     GADCU_CUDA(cudaMalloc(&ctx->gemm_flags, 4096));  // (fewer split tiles than SM pairs: 8 x 74 words)
     GADCU_CUDA(cudaMemset(ctx->gemm_flags, 0, 4096));

@@ -111,8 +111,8 @@ GADCU_API gadcu_status gadcu_ctx_set_lazy(gadcu_ctx* ctx, int enable, uint64_t m
  * tanh VJP on an incoming dA (analytic.rs:385-395), sub(target, add(., tile_as(bias))) (net_ext.rs:110-118) — run on the
  * accumulator in the GEMM's epilogue, which also writes the TF32 operand copies the next product reads. Same op order, one
  * rounding each: values are bit-identical to enable = 0 (every product launched where it is recorded, tails as separate kernels).
- * enable = 1 (default): where it pays — products with more 256 x 256 output tiles than the chip has SM pairs, whose tails then
- * overlap the next tile's MMAs; 2: always; 0: never. */
+ * enable = 1 (default): where it pays — products whose 256 x 256 output tiles keep at least half of the chip's SM pairs busy;
+ * 2: always; 0: never. */
 GADCU_API gadcu_status gadcu_ctx_set_gemm_epilogue(gadcu_ctx* ctx, int enable);
 GADCU_API gadcu_status gadcu_ctx_memory_stats(gadcu_ctx* ctx, uint64_t* bytes_in_use, uint64_t* bytes_reserved,
                                               uint64_t* kernel_launches);
