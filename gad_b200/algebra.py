@@ -290,6 +290,12 @@ class CuArray:
     def device_ptr(self) -> int:
         return int(self.ctx.lib.gadcu_array_device_ptr(self.handle) or 0)
 
+    def force(self) -> "CuArray":
+        """Make sure the bytes exist: a deferred value (an elementwise region, a product that has been recorded but not
+        launched) is computed now, on the context's stream, without a host synchronisation."""
+        self.ctx.lib.gadcu_array_device_ptr(self.handle)
+        return self
+
     def __del__(self):
         try:
             if getattr(self, "handle", None):

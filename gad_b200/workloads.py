@@ -107,7 +107,9 @@ def mlp_hvp(ctx: Context, X: CuArray, Ws, bs, target: CuArray, vs: Sequence[CuAr
     # the second sweep's outputs are what is summed over the ranks: each product travels as soon as the sweep has completed
     # it, while the layers below are still being differentiated (gadcu_compute_gradients_dp)
     second = g.compute_gradients(s.gid(), one, comm if dp and overlap else None)
-    hv, lossd = [second.get(w.gid()).data() for w in vW], loss.data()
+    # GraphN gradients are VALUES — further ops may be recorded on them — so nothing forces them at the end of the sweep the
+    # way Graph1 forces its variables' gradients; the products are this workload's result, so they are computed here
+    hv, lossd = [second.get(w.gid()).data().force() for w in vW], loss.data()
     if dp:
         comm.allreduce_sum(([] if overlap else hv) + [lossd])
     return hv, lossd, g.num_nodes()

@@ -100,8 +100,9 @@ def test_c5_hvp_matches_f64_closed_form_at_tensor_core_shape(ctx):
     hv, loss, nodes = wl.mlp_hvp(ctx, ctx.array(X), [ctx.array(w) for w in Ws], [ctx.array(b) for b in bs], ctx.array(T),
                                  [ctx.array(v) for v in Vs])
     prof = ctx.profile_end()
-    # (22 products are recorded; the ones no requested value depends on are never launched when products are deferred)
-    assert prof["matmul"]["launches"] >= 18 and ctx.launches() > launches
+    # (22 products are recorded; the two no requested value depends on are never launched when products are deferred — at
+    # this shape, too small for deferral, all 22 run)
+    assert prof["matmul"]["launches"] >= 20 and ctx.launches() > launches
     want = mlp_f64.mlp_hvp_f64(X, Ws, bs, T, Vs)
     wl_, _, _ = mlp_f64.mlp_grad_f64(X, Ws, bs, T)
     assert abs(loss.item() - wl_) <= 1e-5 * abs(wl_)
