@@ -123,7 +123,7 @@ struct SymProgram {
       return int32_t(instrs.size() - 1);
     }
     instrs.push_back(i);
-    live.push_back(0);
+    if (array_mode) live.push_back(0);
     return int32_t(instrs.size() - 1);
   }
   std::vector<ArrayRef> run(const std::vector<int32_t>& outs);
@@ -151,7 +151,15 @@ struct SymRef {
     }
   }
 };
-const std::shared_ptr<SymProgram>& program_of(const gadcu_array* a) { return static_cast<SymRef*>(a->sym.get())->prog; }
+// A batched scalar tape makes thousands of handles per recorded step and needs none of the per-register bookkeeping (no
+// column is ever evicted, nothing is written in place under it): its handles hold the program itself. Only the handles of
+// array-mode regions go through a SymRef.
+std::shared_ptr<SymProgram> program_of(const gadcu_array* a) {
+  return a->sym_direct ? std::static_pointer_cast<SymProgram>(a->sym) : static_cast<SymRef*>(a->sym.get())->prog;
+}
+const SymProgram* program_ptr(const gadcu_array* a) {
+  return a->sym_direct ? static_cast<const SymProgram*>(a->sym.get()) : static_cast<SymRef*>(a->sym.get())->prog.get();
+}
 
 ArrayRef sym_array(const std::shared_ptr<SymProgram>& prog, int32_t reg, const Dim4& dims = Dim4(), bool is_scalar = true) {
   auto* a = new gadcu_array;
@@ -160,7 +168,12 @@ ArrayRef sym_array(const std::shared_ptr<SymProgram>& prog, int32_t reg, const D
   a->dtype = prog->dtype;
   a->is_scalar = is_scalar;
   a->ctx = prog->ctx;
-  a->sym = std::make_shared<SymRef>(prog, reg);
+  if (prog->array_mode) {
+    a->sym = std::make_shared<SymRef>(prog, reg);
+  } else {
+    a->sym = prog;
+    a->sym_direct = true;
+  }
   a->sym_reg = reg;
   return ArrayRef(a, false);
 }
@@ -1412,7 +1425,7 @@ class SymAlgebra final : public Algebra {
     if (!v.data) fail(GADCU_ERR_INVALID, "batched tape: value has no data");
     const ArrayRef& a = v.data;
     if (a->sym_reg >= 0 && a->sym) {
-      if (program_of(a.get()).get() != prog_.get()) fail(GADCU_ERR_INVALID, "batched tape: value belongs to another tape");
+      if (program_ptr(a.get()) != prog_.get()) fail(GADCU_ERR_INVALID, "batched tape: value belongs to another tape");
       return a->sym_reg;
     }
     if (a->dtype != prog_->dtype) fail(GADCU_ERR_TYPE, "batched tape: dtype mismatch");
@@ -1548,10 +1561,10 @@ std::shared_ptr<SymProgram> lazy_program(gadcu_ctx* ctx, gadcu_dtype dt, uint64_
 int32_t lazy_operand(const std::shared_ptr<SymProgram>& prog, const ArrayRef& a_in) {
   ArrayRef a = a_in;
   if (a->symbolic()) {
-    if (program_of(a.get()).get() == prog.get()) return a->sym_reg;
+    if (program_ptr(a.get()) == prog.get()) return a->sym_reg;
     a = materialize(a);  // a value of an earlier tape / another size class: read its bytes
   }
-  if (a->sym_reg >= 0 && a->sym && program_of(a.get()).get() == prog.get()) return a->sym_reg;  // forced earlier: the program loads the column
+  if (a->sym_reg >= 0 && a->sym && program_ptr(a.get()) == prog.get()) return a->sym_reg;  // forced earlier: the program loads the column
   int kind = 0;  // 0 dense, 1 uniform, 2 column tile ([1,D] over [B,D]), 3 row tile ([B,1] over [B,D])
   uint64_t d0 = 0;
   if (a->bcast1() || (a->elements() == 1 && prog->lanes != 1)) {

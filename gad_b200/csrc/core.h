@@ -200,6 +200,7 @@ struct gadcu_array {
   // symbolic per-lane value of a batched scalar tape (batched.cu): no buffer until forced
   std::shared_ptr<void> sym;
   int32_t sym_reg = -1;
+  bool sym_direct = false;  // `sym` is the lane program itself (batched scalar tapes: nothing to count per handle); else a per-handle record of it
   bool symbolic() const { return sym_reg >= 0 && !buf; }
 
   void retain() { refs.fetch_add(1, std::memory_order_relaxed); }

@@ -175,6 +175,7 @@ ArrayRef clone_handle(const ArrayRef& src) {
   a->ctx = src->ctx;
   a->sym = src->sym;
   a->sym_reg = src->sym_reg;
+  a->sym_direct = src->sym_direct;
   return ArrayRef(a, false);
 }
 
