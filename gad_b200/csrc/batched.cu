@@ -1553,6 +1553,12 @@ std::shared_ptr<SymProgram> lazy_program(gadcu_ctx* ctx, gadcu_dtype dt, uint64_
   prog->array_mode = true;
   prog->epoch = epoch;
   ctx->lazy_programs[key] = prog;
+  if (ctx->lazy_all.size() >= 64) {  // (drop the records of programs that have died since; lazy_before_write prunes too)
+    size_t keep = 0;
+    for (auto& w : ctx->lazy_all)
+      if (!w.expired()) ctx->lazy_all[keep++] = w;
+    ctx->lazy_all.resize(keep);
+  }
   ctx->lazy_all.emplace_back(prog);
   return prog;
 }
