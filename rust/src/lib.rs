@@ -594,7 +594,20 @@ impl CuGraphN {
         to_result(unsafe { gadcu_compute_gradients(self.h, id.0, id.1, &seed.v, &mut s) }, "compute_gradients")?;
         Ok(CuStore { h: s, _t: PhantomData })
     }
+    /// The same sweep over one batch shard: every variable's gradient is summed over the ranks as soon as the sweep has
+    /// completed it (overlapping the rest of the sweep) and comes back as a constant value.
+    pub fn compute_gradients_dp<T: CuFloat>(&mut self, id: (u32, u32), seed: &CuValue<T>, comm: &CuComm) -> Result<CuStore<T>> {
+        let mut s = std::ptr::null_mut();
+        to_result(unsafe { gadcu_compute_gradients_dp(self.h, id.0, id.1, &seed.v, comm.h, &mut s) }, "compute_gradients_dp")?;
+        Ok(CuStore { h: s, _t: PhantomData })
+    }
 }
+
+/// Backend switches with no counterpart in gad (include/gadcu.h): fused GEMM epilogues (0 never, 1 where it pays, 2 always)
+/// and automatic CUDA-graph replay keyed by the recorded kernel sequence (the tape is still rebuilt every step).
+pub fn set_gemm_epilogue(mode: i32) { unsafe { gadcu_ctx_set_gemm_epilogue(backend().ctx, mode); } }
+pub fn set_auto_replay(on: bool) { unsafe { gadcu_ctx_set_auto_replay(backend().ctx, on as i32); } }
+pub fn flush() { unsafe { gadcu_ctx_flush(backend().ctx); } }
 
 /// One communicator per rank (one process per GPU); the unique id travels through whatever launched the ranks.
 pub struct CuComm { h: *mut gadcu_comm }
