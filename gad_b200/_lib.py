@@ -131,6 +131,7 @@ SIGNATURES = {
     "gadcu_batched_create": (C.c_int, [P, C.c_int, C.c_uint64, PP]),
     "gadcu_batched_force": (C.c_int, [P, VP, PP]),
     "gadcu_batched_program_stats": (C.c_int, [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "gadcu_batched_sweep_memo_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gadcu_comm_unique_id": (C.c_int, [P]),
     "gadcu_comm_init": (C.c_int, [P, C.c_int, C.c_int, P, PP]),
     "gadcu_comm_allreduce_sum": (C.c_int, [P, PP, C.c_size_t]),

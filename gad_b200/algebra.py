@@ -175,6 +175,12 @@ class Context:
         _check(self.lib.gadcu_ctx_memory_stats(self.handle, C.byref(a), C.byref(b), C.byref(c)))
         return {"bytes_in_use": a.value, "bytes_reserved": b.value, "kernel_launches": c.value}
 
+    def sweep_memo_stats(self) -> dict:
+        """Batched sweeps served from the structure table / walked node by node / structures held (process-wide)."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self.lib.gadcu_batched_sweep_memo_stats(C.byref(a), C.byref(b), C.byref(c)))
+        return {"replayed": a.value, "walked": b.value, "structures": c.value}
+
     def launches(self) -> int:
         return self.stats()["kernel_launches"]
 

@@ -346,6 +346,11 @@ class GraphAlgebra final : public Algebra {
   void set_gemm_sink(GemmSink h) { gemm_sink_ = std::move(h); }
   std::unique_ptr<Store> evaluate_gradients(Id id, ArrayRef seed, bool once);
   std::unique_ptr<Store> compute_gradients(Id id, const Value& seed);
+  // batched.cu, sweep memo: everything a reverse sweep reads from the tape, folded into two words (false: the tape holds
+  // something the fold cannot describe — a user-defined VJP, a captured array `register_of` has no register for); and the effect of
+  // a consuming sweep on the nodes it visited (graph.rs:242), for a sweep that was replayed rather than run
+  bool structure_hash(uint64_t out[2], const std::function<int64_t(const gadcu_array&)>& register_of) const;
+  void consume(const std::vector<uint32_t>& node_indices);
 
  private:
   FinalHook final_hook_;

@@ -28,6 +28,7 @@
 // interpreter below as the fallback for batched tapes when NVRTC is unavailable.
 #include <cmath>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <sstream>
 #include <tuple>
@@ -1782,9 +1783,60 @@ std::unique_ptr<GraphAlgebra> make_batched(gadcu_ctx* ctx, gadcu_dtype dt, uint6
   return g;
 }
 
+// ---- sweep memo ---------------------------------------------------------------------------------------------------
+// A gad program records the same tape every step (net_ext.rs:52), and the reverse sweep over a batched tape does nothing but
+// append instructions to the lane program and fill the store with (id -> register): a pure function of the recorded forward
+// instructions, the tape's nodes, the root and the seed's register. So that function is tabulated: the first sweep over a
+// structure runs (GraphAlgebra::sweep through the symbolic algebra, as always) and leaves behind the instruction tail it
+// appended, the store's (id, register) pairs and the nodes it visited; a later sweep over the same structure appends the
+// tail, rebuilds the store from the pairs — every visited id present, as values of the lane program, exactly as the sweep
+// leaves them — and clears the visited nodes if it is a consuming one. What it skips is the walk itself: heap, VJP
+// dispatch, accumulation, a thousand handle objects (0.3 ms of the 0.41 ms a recorded Rosenbrock-64 call took).
+struct SweepMemo {
+  std::vector<SymInstr> tail;
+  std::vector<std::pair<uint32_t, int32_t>> store_regs;  // ascending node index -> register of its gradient
+};
+std::mutex g_sweeps_mu;
+std::unordered_map<PlanKey, SweepMemo, PlanKeyHash> g_sweeps;
+std::atomic<uint64_t> g_sweeps_replayed{0}, g_sweeps_walked{0};
+
+bool sweep_key(const SymProgram& P, const GraphAlgebra& g, Id id, const gadcu_array& seed, bool once, PlanKey& k) {
+  const int32_t seed_reg = seed.sym_reg;
+  uint64_t nodes[2];
+  // a captured real array (a variable's column) is known to the program once the forward pass has loaded it; one the sweep
+  // would be the first to load makes the sweep more than a function of the structure, and is not tabulated
+  auto register_of = [&](const gadcu_array& a) -> int64_t {
+    if (!a.buf || a.dtype != P.dtype) return -1;
+    auto it = P.input_reg.find(std::make_tuple(static_cast<const void*>(a.ptr()), a.phys.elements() == 1 ? 1 : 0, uint64_t(0)));
+    return it == P.input_reg.end() ? -1 : it->second;
+  };
+  if (P.array_mode || !g.structure_hash(nodes, register_of)) return false;
+  k.words.clear();
+  k.words.reserve(P.instrs.size() * 4 + 8);
+  k.words.push_back(uint64_t(P.dtype) | uint64_t(once) << 8 | uint64_t(id.index) << 16);
+  k.words.push_back(uint64_t(uint32_t(seed_reg)) | uint64_t(P.instrs.size()) << 32);
+  k.words.push_back(nodes[0]);
+  k.words.push_back(nodes[1]);
+  k.words.push_back(uint64_t(seed.dtype) | uint64_t(seed.is_scalar) << 8);  // (what the sweep checks the root's gradient for)
+  for (int i = 0; i < 4; i++) k.words.push_back(seed.dims[i]);
+  for (const SymInstr& I : P.instrs) {
+    uint64_t bits;
+    std::memcpy(&bits, &I.imm, 8);
+    k.words.push_back(uint64_t(I.op) | uint64_t(uint32_t(I.a)) << 16);
+    k.words.push_back(uint64_t(uint32_t(I.b)) | uint64_t(uint32_t(I.c)) << 32);
+    k.words.push_back(uint64_t(uint32_t(I.d)));
+    k.words.push_back(bits);
+  }
+  uint64_t h = 1469598103934665603ull;
+  for (uint64_t w : k.words) { h ^= w; h *= 1099511628211ull; }
+  k.hash = h;
+  return true;
+}
+
 std::unique_ptr<Store> batched_evaluate_gradients(GraphAlgebra& g, Id id, ArrayRef seed, bool once) {
   auto* sym = dynamic_cast<SymAlgebra*>(&g.eval());
   if (!sym) fail(GADCU_ERR_INVALID, "not a batched tape");
+  if (id.index == 0 || id.index > g.num_nodes()) fail(GADCU_ERR_MISSING_NODE, "Trying to obtain a node from an incorrect `id`.");
   Value sseed = seed->sym_reg >= 0 ? Value(seed) : sym->load(seed);
   // which ids are variables must be asked before a consuming sweep clears the nodes
   std::vector<Id> var_ids;
@@ -1792,7 +1844,57 @@ std::unique_ptr<Store> batched_evaluate_gradients(GraphAlgebra& g, Id id, ArrayR
     Id vid{id.arena, i};
     if (g.is_variable(vid)) var_ids.push_back(vid);
   }
-  std::unique_ptr<Store> store = g.evaluate_gradients(id, sseed.data, once);
+  static const bool memo_on = [] { const char* e = getenv("GADCU_SWEEP_MEMO"); return !e || atoi(e) != 0; }();
+  const std::shared_ptr<SymProgram>& prog0 = sym->program();
+  PlanKey skey;
+  const bool keyed = memo_on && sseed.data->sym_reg >= 0 && sweep_key(*prog0, g, id, *sseed.data, once, skey);
+  std::unique_ptr<Store> store;
+  if (keyed) {
+    const SweepMemo* hit = nullptr;
+    SweepMemo copy;
+    {
+      std::lock_guard<std::mutex> lk(g_sweeps_mu);
+      auto it = g_sweeps.find(skey);
+      if (it != g_sweeps.end()) { copy = it->second; hit = &copy; }
+    }
+    if (hit) {
+      {
+        std::lock_guard<std::mutex> lk(prog0->mu);
+        prog0->instrs.insert(prog0->instrs.end(), hit->tail.begin(), hit->tail.end());
+      }
+      store = std::make_unique<Store>();
+      std::vector<uint32_t> visited;
+      visited.reserve(hit->store_regs.size());
+      auto hint = store->values.end();
+      for (auto& pr : hit->store_regs) {
+        hint = store->values.emplace_hint(hint, Id{id.arena, pr.first}, Value(sym_array(prog0, pr.second)));
+        visited.push_back(pr.first);
+      }
+      if (once) g.consume(visited);
+      g_sweeps_replayed++;
+    }
+  }
+  if (!store) {
+    const size_t n_before = prog0->instrs.size();
+    store = g.evaluate_gradients(id, sseed.data, once);
+    g_sweeps_walked++;
+    if (keyed) {
+      SweepMemo m;
+      bool ok = true;
+      for (auto& kv : store->values) {
+        const ArrayRef& d = kv.second.data;
+        if (kv.first.arena != id.arena || !d || !(d->sym_reg >= 0 && d->sym) || program_ptr(d.get()) != prog0.get() || d->buf) { ok = false; break; }
+        m.store_regs.emplace_back(kv.first.index, d->sym_reg);
+      }
+      if (ok) {
+        std::lock_guard<std::mutex> lk(prog0->mu);
+        m.tail.assign(prog0->instrs.begin() + long(n_before), prog0->instrs.end());
+        std::lock_guard<std::mutex> lk2(g_sweeps_mu);
+        if (g_sweeps.size() >= 64) g_sweeps.clear();
+        g_sweeps.emplace(std::move(skey), std::move(m));
+      }
+    }
+  }
   // one kernel for the gradients of all variables
   std::vector<int32_t> regs;
   std::vector<Id> ids;
@@ -1890,6 +1992,15 @@ gadcu_status gadcu_batched_rerun(gadcu_store* s, gadcu_array* const* columns, si
     std::vector<ArrayRef> grads = batched_rerun(*s, cols);
     for (size_t i = 0; i < grads.size(); i++) gradients_out[i] = grads[i] ? grads[i].detach() : nullptr;
   });
+}
+gadcu_status gadcu_batched_sweep_memo_stats(uint64_t* replayed, uint64_t* walked, uint64_t* structures) {
+  if (replayed) *replayed = g_sweeps_replayed.load();
+  if (walked) *walked = g_sweeps_walked.load();
+  if (structures) {
+    std::lock_guard<std::mutex> lk(g_sweeps_mu);
+    *structures = g_sweeps.size();
+  }
+  return GADCU_OK;
 }
 gadcu_status gadcu_batched_program_stats(const gadcu_store* s, uint64_t* instructions, uint64_t* slots) {
   if (instructions) *instructions = s->program_instructions;

@@ -12,6 +12,8 @@
 #include "batched.h"
 
 #include <algorithm>
+#include <cstring>
+#include <functional>
 
 using namespace gadcu;
 
@@ -737,6 +739,42 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
     }
   if (hooked) waiting_.clear();
   return store;
+}
+
+bool GraphAlgebra::structure_hash(uint64_t out[2], const std::function<int64_t(const gadcu_array&)>& register_of) const {
+  uint64_t h1 = 1469598103934665603ull, h2 = 0x9E3779B97F4A7C15ull;
+  auto mix = [&](uint64_t w) {
+    h1 = (h1 ^ w) * 1099511628211ull;
+    h2 = (h2 + w) * 0xff51afd7ed558ccdull;
+    h2 ^= h2 >> 33;
+  };
+  if (final_hook_ || higher_order_) return false;
+  mix(nodes_.size());
+  for (const Node& n : nodes_) {
+    if (n.op == Op::CUSTOM || n.custom) return false;
+    uint64_t cbits;
+    std::memcpy(&cbits, &n.c, 8);
+    mix(uint64_t(n.op) | uint64_t(n.has_update) << 8 | uint64_t(n.c_is_int) << 9 | uint64_t(n.flag) << 10 | uint64_t(n.p1.transposed) << 11 |
+        uint64_t(n.p2.transposed) << 12 | uint64_t(n.fwd_scalar) << 13 | uint64_t(n.fwd_dtype) << 14 | uint64_t(n.inputs.size()) << 16 |
+        uint64_t(n.saved.size()) << 40);
+    mix(cbits);
+    for (int i = 0; i < 4; i++) mix(n.d[i] * 31 + n.fwd_dims[i]);
+    for (const Id& in : n.inputs) mix(in.index);
+    for (const Value& v : n.saved) {
+      int64_t r = -1;
+      if (v.data) r = v.data->sym_reg >= 0 && v.data->sym ? v.data->sym_reg : register_of(*v.data);
+      if (v.data && r < 0) return false;  // (a captured value the lane program does not know by register yet)
+      mix(uint64_t(uint32_t(r)) | uint64_t(v.id.index) << 32);
+    }
+  }
+  out[0] = h1;
+  out[1] = h2;
+  return true;
+}
+
+void GraphAlgebra::consume(const std::vector<uint32_t>& node_indices) {
+  for (uint32_t i : node_indices)
+    if (i >= 1 && i <= nodes_.size()) nodes_[i - 1].clear();
 }
 
 // graph.rs:263-290: the gradient algebra is a clone of the eval algebra; gradients are pure data.

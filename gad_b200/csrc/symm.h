@@ -22,9 +22,9 @@ struct SymmRegion {
   size_t mapped_bytes = 0;
 };
 
-// Collective over the communicator's ranks (every rank calls it at the same point). `allreduce_min` sums... no: takes this
-// rank's int and returns the MINIMUM over ranks (used as "did everybody succeed" and as a barrier); `allgather` gathers
-// `bytes` bytes per rank (host buffers). Both are provided by comm.cu on top of NCCL.
+// Collectives over the communicator's ranks (every rank calls them at the same point). `allreduce_min` takes this rank's
+// int and returns the minimum over ranks (used as "did everybody succeed" and as a barrier); `allgather` gathers `bytes`
+// bytes per rank (host buffers). Both are provided by comm.cu on top of NCCL.
 struct SymmCollectives {
   std::function<int(int)> allreduce_min;
   std::function<void(const void* mine, void* all, size_t bytes)> allgather;

@@ -295,6 +295,10 @@ GADCU_API gadcu_status gadcu_batched_force(gadcu_algebra* g, const gadcu_value* 
  * column of the i-th variable (+1 reference; NULL where the sweep produced none). `s` must come from a batched sweep. */
 GADCU_API gadcu_status gadcu_batched_rerun(gadcu_store* s, gadcu_array* const* columns, size_t n, gadcu_array** gradients_out);
 GADCU_API gadcu_status gadcu_batched_program_stats(const gadcu_store* s, uint64_t* instructions, uint64_t* slots);
+/* A batched sweep over a tape structure seen before (same recorded instructions, nodes, root and seed kind) is not walked
+ * again: the instructions it appended and the store it filled are replayed from a process-wide table (GADCU_SWEEP_MEMO=0
+ * turns that off). Counters since process start: sweeps served from the table, sweeps walked, structures held. */
+GADCU_API gadcu_status gadcu_batched_sweep_memo_stats(uint64_t* replayed, uint64_t* walked, uint64_t* structures);
 
 /* ---- data parallelism over the batch dimension (new: the reference is single-process) ------------
  * apply_gradient_step sums per-example gradients (net_ext.rs:62-65), so sharding the batch and

@@ -196,6 +196,7 @@ extern "C" {
     pub fn gadcu_batched_force(g: A, v: V, out: *mut *mut gadcu_array) -> gadcu_status;
     pub fn gadcu_batched_rerun(s: *mut gadcu_store, columns: *const *mut gadcu_array, n: usize, gradients_out: *mut *mut gadcu_array) -> gadcu_status;
     pub fn gadcu_batched_program_stats(s: *const gadcu_store, instructions: *mut u64, slots: *mut u64) -> gadcu_status;
+    pub fn gadcu_batched_sweep_memo_stats(replayed: *mut u64, walked: *mut u64, structures: *mut u64) -> gadcu_status;
     // data parallelism
     pub fn gadcu_comm_allreduce_sum_async(comm: *mut gadcu_comm, arrays: *const *mut gadcu_array, n: usize) -> gadcu_status;
     pub fn gadcu_comm_join(comm: *mut gadcu_comm) -> gadcu_status;

@@ -56,6 +56,67 @@ def test_batched_rerun_at_new_points_equals_a_fresh_tape(ctx, oracle):
         store.rerun([ctx.array(x1[0])])
 
 
+def test_batched_sweep_over_a_known_structure_is_replayed_not_walked(ctx, oracle):
+    """The sweep memo (batched.cu): a second tape of the same structure gets the first one's backward instructions and
+    store layout without walking the nodes — same bits, same store ids, same consumption of the tape; a tape that
+    differs in one constant, in the root, or in the kind of sweep is walked."""
+    n, lanes = 12, 515
+    rng = np.random.default_rng(11)
+    xs = [-1.2 + 2.4 * rng.random((n, lanes)) for _ in range(3)]
+
+    def record(x, scale=100, once=True, root_last=True):
+        g = gb.BatchedGraph1(ctx, lanes, gb.F64)
+        vs = [g.variable(ctx.array(x[i])) for i in range(n)]
+        terms = []
+        for i in range(n - 1):
+            d = g.sub(vs[i + 1], g.mul(vs[i], vs[i]))
+            e = g.addc(g.neg(vs[i]), 1)
+            terms.append(g.add(g.mulc(g.mul(d, d), scale), g.mul(e, e)))
+        f = g.add_all(terms if root_last else terms[:-1])
+        store = (g.evaluate_gradients_once if once else g.evaluate_gradients)(f.gid(), 1.0)
+        return g, f, vs, store
+
+    def grads(vs, store):
+        got = [store.get(v.gid()) for v in vs]  # (None: a variable the root does not depend on)
+        return np.stack([to_np(c)[:, 0, 0, 0] if c is not None else np.zeros(lanes) for c in got])
+
+    s0 = ctx.sweep_memo_stats()
+    g1, f1, v1, st1 = record(xs[0])
+    s1 = ctx.sweep_memo_stats()
+    g2, f2, v2, st2 = record(xs[1])
+    s2 = ctx.sweep_memo_stats()
+    assert s1["walked"] - s0["walked"] + s1["replayed"] - s0["replayed"] == 1
+    assert (s2["replayed"] - s1["replayed"], s2["walked"] - s1["walked"]) == (1, 0)
+    for x, vs, st in ((xs[0], v1, st1), (xs[1], v2, st2)):
+        _, ograd, _ = oracle.rosenbrock_batch(x, nthreads=2)
+        assert np.array_equal(grads(vs, st), ograd)
+    assert st1.ids() == st2.ids()
+    assert len(st2.ids()) == g2.num_nodes()
+    assert st2.program_stats() == st1.program_stats()
+    # the replayed sweep consumed the tape like the walked one: a second sweep finds the root without its update
+    for g, f in ((g1, f1), (g2, f2)):
+        again = g.evaluate_gradients_once(f.gid(), 1.0)
+        assert len(again.ids()) == 1
+    # the re-run of a replayed sweep's program
+    re = st2.rerun([ctx.array(xs[2][i]) for i in range(n)])
+    _, ograd2, _ = oracle.rosenbrock_batch(xs[2], nthreads=2)
+    assert np.array_equal(np.stack([to_np(c)[:, 0, 0, 0] for c in re]), ograd2)
+    # other structures are walked: another constant, another root, a non-consuming sweep (which can be swept twice)
+    for kw in ({"scale": 99}, {"root_last": False}, {"once": False}):
+        before = ctx.sweep_memo_stats()
+        g, f, vs, st = record(xs[0], **kw)
+        after = ctx.sweep_memo_stats()
+        assert after["walked"] - before["walked"] == 1, kw
+        g_, f_, vs_, st_ = record(xs[0], **kw)
+        assert ctx.sweep_memo_stats()["replayed"] - after["replayed"] == 1, kw
+        assert np.array_equal(grads(vs, st), grads(vs_, st_))
+        if kw.get("scale") == 99:
+            assert not np.array_equal(grads(vs, st), grads(v1, st1))
+        if kw.get("once") is False:
+            twice = g_.evaluate_gradients(f_.gid(), 1.0)
+            assert np.array_equal(grads(vs_, twice), grads(vs_, st_))
+
+
 def test_wide_batched_tape_beyond_4k_of_kernel_parameters(ctx, oracle):
     """Rosenbrock-320: 320 input and 320 output columns (5 KB of pointers) + 640 constants in one lane program."""
     n, lanes = 320, 64
