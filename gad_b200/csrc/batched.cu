@@ -127,9 +127,18 @@ struct SymProgram {
     if (array_mode) live.push_back(0);
     return int32_t(instrs.size() - 1);
   }
+  // array mode: reduce one register over contiguous segments of `reduce` lanes instead of writing it — the cut and the
+  // order inside a chunk are reduce.cu's (k::reduce_contig_plan), so the bits are those of materialise-then-reduce
+  struct ReduceSpec {
+    k::RedOp op;
+    uint64_t reduce, outer, splits, chunk;
+    bool vec;    // what reduce.cu would choose for the materialised value: reduce % V == 0
+    void* out;   // [outer * splits] partials (or the result itself when splits == 1)
+  };
   std::vector<ArrayRef> run(const std::vector<int32_t>& outs);
   std::vector<ArrayRef> run_interpreter(const std::vector<int32_t>& todo);
-  std::vector<ArrayRef> run_jit(const std::vector<int32_t>& todo);
+  std::vector<ArrayRef> run_jit(const std::vector<int32_t>& todo, const ReduceSpec* red = nullptr, bool* red_done = nullptr);
+  bool run_reduce(int32_t reg, ReduceSpec& spec);
 };
 
 // What a symbolic handle holds: keeps the program alive and counts the handles per register, so that a write
@@ -529,6 +538,9 @@ struct JitPlan {
   // registers and at 8 loads in flight per thread by the same budget)
   int ring = 0, stage_blocks = 0;  // ring depth; resident blocks per SM the kernel is compiled for (its register budget)
   size_t smem_bytes = 0;
+  // the one output is not stored but reduced (SymProgram::ReduceSpec): 0 no, 1 sum, 2 max; td[] carries reduce, chunk, splits
+  int red = 0;
+  size_t red_td = 0;  // index of `reduce` in td[] (chunk and splits follow)
 };
 
 thread_local const JitPlan* g_plan = nullptr;  // the plan being rendered by this thread
@@ -713,6 +725,62 @@ std::string gen_source(const SymProgram& P, const JitPlan& J, const std::unorder
     return J.idx32 ? "(unsigned)(" + i + ") / (unsigned)p.td[" + std::to_string(k) + "]" : "(" + i + ") / p.td[" + std::to_string(k) + "]";
   };
   const char* lanes4[] = {".x", ".y", ".z", ".w"};
+  if (J.red) {
+    // ---- reducing skeleton: reduce.cu's reduce_contig_kernel with the elementwise chain in place of the load. One block
+    // per (segment, chunk); 256 threads walk the chunk with a stride of 256 vectors keeping the V vector lanes apart,
+    // lanes combined in order, butterfly over the warp, the 8 warps in order. Same cut, same order => same bits.
+    const std::string td = "p.td[" + std::to_string(J.red_td) + "]", tdc = "p.td[" + std::to_string(J.red_td + 1) + "]",
+                      tds = "p.td[" + std::to_string(J.red_td + 2) + "]";
+    o << (J.red == 1 ? "#define COMB(a, b) ((a) + (b))\n#define IDENT T(0)\n" : "#define COMB(a, b) ((b) > (a) ? (b) : (a))\n") << (J.red == 1 ? "" : f32 ? "#define IDENT (-__int_as_float(0x7f800000))\n" : "#define IDENT (-__longlong_as_double(0x7ff0000000000000ll))\n");
+    o << "extern \"C\" __global__ void __launch_bounds__(256" << (J.stage_blocks ? ", " + std::to_string(J.stage_blocks) : std::string()) << ") lane_program(const P p) {\n";
+    o << "  __shared__ T warp_part[8];\n";
+    o << "  const u64 reduce = " << td << ", chunk = " << tdc << ", splits = " << tds << ";\n";
+    o << "  const u64 seg = blockIdx.x / splits, split = blockIdx.x % splits;\n";
+    o << "  const u64 lo = split * chunk;\n  u64 hi = lo + chunk;\n  if (hi > reduce) hi = reduce;\n  const u64 base = seg * reduce;\n";
+    for (auto& d : J.uniform) o << "  const T " << reg_name(d.first) << " = p.in[" << d.second << "][0];\n";
+    o << "  T v = IDENT;\n  if (lo < hi) {\n";
+    if (J.V > 1) {
+      o << "    const u64 vbase = base / " << J.V << ", vlo = lo / " << J.V << ", vhi = hi / " << J.V << ";\n";
+      for (int l = 0; l < J.V; l++) o << "    T acc" << l << " = IDENT;\n";
+      // RU steps of a thread's walk at a time: all their loads first, then the chain and the accumulation step by step in
+      // walk order (the order of the additions is what fixes the bits, not when the loads were issued)
+      const int RU = J.U;
+      o << "    for (u64 walk = vlo + threadIdx.x; walk < vhi; walk += " << 256 * RU << ") {\n";
+      for (auto& d : J.dense) o << "      TV v" << J.local.at(d.first) << "[" << RU << "];\n";
+      o << "#pragma unroll\n      for (int u = 0; u < " << RU << "; u++) {\n        const u64 vi = walk + u * 256;\n        if (vi < vhi) {\n";
+      for (auto& d : J.dense) o << "          v" << J.local.at(d.first) << "[u] = __ldcs(reinterpret_cast<const TV*>(p.in[" << d.second << "]) + vbase + vi);\n";
+      o << "        }\n      }\n";
+      o << "#pragma unroll\n      for (int u = 0; u < " << RU << "; u++) {\n        const u64 vi = walk + u * 256;\n        if (vi < vhi) {\n          const u64 gi = vbase + vi;\n";
+      for (size_t k = 0; k < J.col.size(); k++)
+        o << "          const T " << reg_name(J.col[k].first) << " = p.in[" << J.col[k].second << "][" << col_index(k, "gi * " + std::to_string(J.V)) << "];\n";
+      for (int l = 0; l < J.V; l++) {
+        o << "          T y" << l << ";\n          body(p, gi * " << J.V << " + " << l;
+        for (auto& d : J.dense) o << ", v" << J.local.at(d.first) << "[u]" << lanes4[l];
+        for (auto& d : J.uniform) o << ", " << reg_name(d.first);
+        for (auto& d : J.col) o << ", " << reg_name(d.first);
+        o << ", y" << l << ");\n";
+      }
+      for (int l = 0; l < J.V; l++) o << "          acc" << l << " = COMB(acc" << l << ", y" << l << ");\n";
+      o << "        }\n      }\n    }\n    v = acc0;\n";
+      for (int l = 1; l < J.V; l++) o << "    v = COMB(v, acc" << l << ");\n";
+    } else {
+      o << "    for (u64 i = lo + threadIdx.x; i < hi; i += 256) {\n      const u64 gi = base + i;\n";
+      for (auto& d : J.dense) o << "      const T s" << J.local.at(d.first) << " = p.in[" << d.second << "][gi];\n";
+      for (size_t k = 0; k < J.col.size(); k++)
+        o << "      const T " << reg_name(J.col[k].first) << " = p.in[" << J.col[k].second << "][" << col_index(k, "gi") << "];\n";
+      o << "      T y;\n      body(p, gi";
+      for (auto& d : J.dense) o << ", s" << J.local.at(d.first);
+      for (auto& d : J.uniform) o << ", " << reg_name(d.first);
+      for (auto& d : J.col) o << ", " << reg_name(d.first);
+      o << ", y);\n      v = COMB(v, y);\n    }\n";
+    }
+    o << "  }\n";
+    o << "#pragma unroll\n  for (int off = 16; off > 0; off >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, v, off); v = COMB(v, w); }\n";
+    o << "  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;\n  __syncthreads();\n";
+    o << "  if (threadIdx.x == 0) {\n    T r = warp_part[0];\n#pragma unroll\n    for (int w = 1; w < 8; w++) r = COMB(r, warp_part[w]);\n"
+         "    p.out[0][seg * splits + split] = r;\n  }\n}\n";
+    return o.str();
+  }
   if (J.ring) {
     // ---- ring-fed skeleton (array mode, large regions): a producer warp streams the dense inputs, tile by tile
     // (BLOCK vectors of 16 bytes per input = 8 KB bulk copies), through a shared-memory ring with cp.async.bulk +
@@ -903,9 +971,9 @@ PlanKey plan_key(const SymProgram& P, const std::vector<int32_t>& todo) {
   return k;
 }
 
-std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
+std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo, const ReduceSpec* red, bool* red_done) {
   const int32_t n = int32_t(instrs.size());
-  const bool reusable = !array_mode && cache.empty();
+  const bool reusable = !array_mode && cache.empty() && !red;
   PlanKey pkey;
   if (reusable) {
     auto it = compiled.find(todo);
@@ -984,7 +1052,23 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   J.U = J.V == 1 ? 1 : (streams <= 4 && J.order.size() <= 64 ? 4 : (streams <= 8 && J.order.size() <= 128 ? 2 : 1));
   J.block = J.order.size() > 256 ? 128 : 256;
   J.idx32 = lanes < (1ull << 32);
-  if (array_mode && J.V == vmax && J.order.size() <= 256 && !J.dense.empty() && J.dense.size() <= 4 && lanes >= (1ull << 22)) {
+  if (red) {
+    // the reducing shape exists for regions short enough to sit in one `body`, with the vector width reduce.cu would
+    // use on the materialised value (anything else: the caller materialises and reduces as before)
+    bool aligned = true;
+    for (auto& d : J.dense) aligned = aligned && (reinterpret_cast<uintptr_t>(J.in_ptrs[size_t(d.second)]) & 15) == 0;
+    if (J.order.size() > 256 || (red->vec && (J.V != vmax || !aligned || red->reduce % uint64_t(vmax) != 0))) return {};
+    if (!red->vec) J.V = 1;
+    static const int red_unroll = [] { const char* e = getenv("GADCU_REDUCE_UNROLL"); return e ? std::max(1, atoi(e)) : 4; }();
+    J.U = J.V == 1 ? 1 : (J.dense.size() <= 4 ? red_unroll : 1);  // loads in flight per thread (see gen_source)
+    J.block = 256;
+    J.red = red->op == k::RedOp::SUM ? 1 : 2;
+    J.red_td = J.tile_d0.size();
+    J.tile_d0.push_back(red->reduce);
+    J.tile_d0.push_back(red->chunk);
+    J.tile_d0.push_back(red->splits);
+  }
+  if (!red && array_mode && J.V == vmax && J.order.size() <= 256 && !J.dense.empty() && J.dense.size() <= 4 && lanes >= (1ull << 22)) {
     // large region: feed the dense inputs through a shared-memory ring (see gen_source). 512-thread tiles, ring of 4
     // (8 with more than two inputs: two tiles' worth in flight), two blocks per SM if the registers allow.
     static const int region_ring = [] { const char* e = getenv("GADCU_REGION_RING"); return e ? atoi(e) : 1; }();
@@ -997,7 +1081,7 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
       J.smem_bytes = size_t(J.ring) * 512 * 16 + size_t(J.ring) * 16;
     }
   }
-  if (J.V == 1 && J.order.size() > 256) {
+  if (!red && J.V == 1 && J.order.size() > 256) {
     // greedy list scheduling for few live values: among the ready instructions take the one that ends the most
     // live ranges (net of the one it starts); prefer computing over loading, then tape order
     J.flat = true;
@@ -1137,7 +1221,7 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   std::string key;
   key.reserve(J.order.size() * 24 + 64);
   key += dtype == GADCU_F32 ? "f32" : "f64";
-  key += "|V" + std::to_string(J.V) + "U" + std::to_string(J.U) + "B" + std::to_string(J.block) + (J.idx32 ? "i32" : "i64") + (J.flat ? "flat" : "") + (J.ring ? "ring" + std::to_string(J.ring) : "");
+  key += "|V" + std::to_string(J.V) + "U" + std::to_string(J.U) + "B" + std::to_string(J.block) + (J.idx32 ? "i32" : "i64") + (J.flat ? "flat" : "") + (J.ring ? "ring" + std::to_string(J.ring) : "") + (J.red ? "red" + std::to_string(J.red) : "");
   auto L = [&](int32_t r) { return r < 0 ? std::string("-") : std::to_string(J.local.at(r)); };
   auto list = [&](const char* tag, const std::vector<std::pair<int32_t, int>>& v) {
     key += tag;
@@ -1170,7 +1254,17 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
     return kernel;
   };
   const jit::Kernel* kernel = nullptr;
-  if (J.ring) {
+  if (J.red) {
+    // reduce.cu cuts a long segment into 8 chunks per SM: compiled for 8 resident blocks (32 registers) they all run at
+    // once; if the chain does not fit that budget, whatever the compiler needs (the chunks then take two rounds)
+    static const int want = [] { const char* e = getenv("GADCU_REDUCE_MINBLOCKS"); return e ? atoi(e) : 8; }();
+    const std::vector<int> candidates = want > 0 ? std::vector<int>{want, 0} : std::vector<int>{0};
+    for (size_t c = 0; c < candidates.size(); c++) {
+      J.stage_blocks = candidates[c];
+      kernel = build(key + "|b" + std::to_string(J.stage_blocks));
+      if (kernel->local_bytes == 0) break;
+    }
+  } else if (J.ring) {
     // the staged kernel is compiled for as many resident blocks per SM as its registers allow without spilling:
     // 5 (<= 80 registers), else 3 (<= 136), else 2; the choice is remembered per structure
     static std::mutex chosen_mu;
@@ -1214,6 +1308,21 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo) {
   }
   // 4. outputs + parameter block (layout of `struct P`: every field is 8 bytes wide)
   std::vector<ArrayRef> out_cols;
+  if (red) {
+    const size_t NI = std::max<size_t>(J.in_ptrs.size(), 1), NT = J.tile_d0.size(), NM = std::max<size_t>(J.imms.size(), 1);
+    std::vector<uint64_t> params(NI + 1 + 1 + NT + NM, 0);
+    for (size_t i = 0; i < J.in_ptrs.size(); i++) params[i] = reinterpret_cast<uint64_t>(J.in_ptrs[i]);
+    params[NI] = reinterpret_cast<uint64_t>(red->out);
+    params[NI + 1] = lanes;
+    for (size_t i = 0; i < NT; i++) params[NI + 2 + i] = J.tile_d0[i];
+    for (size_t i = 0; i < J.imms.size(); i++) std::memcpy(&params[NI + 2 + NT + i], &J.imms[i], 8);
+    if (params.size() * 8 > kMaxParamBytes) return {};
+    ProfileScope prof_scope(ctx, PROF_REDUCE);
+    void* args[] = {params.data()};
+    jit::launch(ctx, kernel, unsigned(red->splits * red->outer), 256u, args, 0);
+    if (red_done) *red_done = true;
+    return {};
+  }
   for (size_t j = 0; j < todo.size(); j++) out_cols.push_back(new_array(ctx, dtype, Dim4(lanes)));
   const size_t NI = std::max<size_t>(J.in_ptrs.size(), 1), NO = std::max<size_t>(J.outs.size(), 1), NT = std::max<size_t>(J.tile_d0.size(), 1),
                NM = std::max<size_t>(J.imms.size(), 1);
@@ -1514,6 +1623,41 @@ class SymAlgebra final : public Algebra {
 };
 
 }  // namespace
+
+bool SymProgram::run_reduce(int32_t reg, ReduceSpec& spec) {
+  std::lock_guard<std::mutex> lk(mu);
+  if (!array_mode || cache.count(reg)) return false;
+  if (!pending.empty()) {
+    resolve_pending({reg});  // products the value depends on are launched now; if that settled the value itself, it exists
+    if (cache.count(reg)) return false;
+  }
+  bool done = false;
+  run_jit({reg}, &spec, &done);
+  return done;
+}
+
+// sum_as / max_as over leading axes of a value that is still a deferred elementwise chain: one kernel computes the chain
+// and reduces it, the value itself is never written (C3 forward: d = exp(x) log(y) + x only feeds the sum; an MLP loss:
+// the squared residual only feeds the sum). Returns null when the value exists already or the shape is not covered.
+ArrayRef lazy_reduce(gadcu_ctx* ctx, k::RedOp op, const ArrayRef& v, uint64_t reduce, uint64_t outer, const Dim4& out_dims) {
+  static const bool on = [] { const char* e = getenv("GADCU_FUSE_REDUCE"); return !e || atoi(e) != 0; }();
+  if (!on || !v->symbolic() || !v->sym || reduce == 0 || outer == 0 || outer > 65535) return ArrayRef();
+  std::shared_ptr<SymProgram> prog = program_of(v.get());
+  if (!prog || !prog->array_mode || prog->lanes != reduce * outer || !lazy_enabled(ctx, prog->lanes, false)) return ArrayRef();
+  SymProgram::ReduceSpec spec;
+  spec.op = op;
+  spec.reduce = reduce;
+  spec.outer = outer;
+  k::reduce_contig_plan(ctx, prog->dtype, reduce, outer, &spec.splits, &spec.chunk);
+  if (spec.splits * outer > 0x7fffffffull) return ArrayRef();
+  spec.vec = reduce % uint64_t(prog->dtype == GADCU_F32 ? 4 : 2) == 0;
+  ArrayRef out = new_array(ctx, prog->dtype, out_dims);
+  ArrayRef partials = spec.splits > 1 ? new_array(ctx, prog->dtype, Dim4(spec.splits * outer)) : out;
+  spec.out = partials->ptr();
+  if (!prog->run_reduce(v->sym_reg, spec)) return ArrayRef();
+  if (spec.splits > 1) k::launch_reduce_partials(ctx, prog->dtype, op, partials->ptr(), out->ptr(), spec.splits, outer);
+  return out;
+}
 
 ArrayRef force_symbolic(const ArrayRef& a) {
   if (!a->symbolic()) return a;

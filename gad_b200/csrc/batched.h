@@ -20,6 +20,9 @@ ArrayRef lazy_elementwise(gadcu_ctx* ctx, k::EwOp op, const ArrayRef& acc, const
 // a matmul recorded as a leaf of the region of its result (launched when something needs it, with the elementwise tail
 // behind it in the GEMM's epilogue where that is one of the known ones: GemmEpilogue)
 ArrayRef lazy_matmul(gadcu_ctx* ctx, const ArrayRef& a, const ArrayRef& b, MatProp p1, MatProp p2, const Dim4& rd, bool fusable);
+// sum / max of a still-deferred value over contiguous segments ([reduce, outer] view), fused into the kernel that computes
+// it, bit-identical to materialise + k::launch_reduce; null when not applicable (the caller takes the ordinary path)
+ArrayRef lazy_reduce(gadcu_ctx* ctx, k::RedOp op, const ArrayRef& v, uint64_t reduce, uint64_t outer, const Dim4& out_dims);
 void lazy_before_write(gadcu_ctx* ctx, const void* buffer);
 void lazy_flush(const std::vector<ArrayRef>& values);
 

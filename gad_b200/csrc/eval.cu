@@ -313,6 +313,24 @@ Value EvalAlgebra::tile_as(const Value& v, const Dim4& rd) {  // array.rs:76-84
 // Reduce every axis where rd differs from v (rd[i] == 1). Consecutive reduced axes form one pass
 // (the reference issues one af::sum / af::max per axis: array.rs:91-96, array_compare.rs:42-47).
 ArrayRef EvalAlgebra::reduce_as(k::RedOp op, const ArrayRef& vin, const Dim4& rd, ArrayRef acc) {
+  if (!acc && vin->symbolic() && !vin->lazy() && rd != vin->dims) {
+    // a deferred elementwise value reduced over its leading axes only (one pass, contiguous segments): computed and
+    // reduced by one kernel, never written
+    const Dim4& d = vin->dims;
+    int last = -1;
+    bool leading = true;
+    for (int i = 0; i < 4; i++)
+      if (rd[i] != d[i]) { leading = leading && i == last + 1; last = i; }
+    if (leading) {
+      uint64_t red = 1, outer = 1;
+      for (int i = 0; i <= last; i++) red *= d[i];
+      for (int i = last + 1; i < 4; i++) outer *= d[i];
+      Dim4 nd = d;
+      for (int i = 0; i <= last; i++) nd[i] = 1;
+      ArrayRef r = lazy_reduce(ctx, op, vin, red, outer, nd);
+      if (r) return r;
+    }
+  }
   ArrayRef cur = materialize(vin);
   Dim4 cd = cur->dims;
   std::vector<std::pair<int, int>> runs;  // [first, last] axis of each run of reduced axes

@@ -64,6 +64,10 @@ enum class RedOp : int { SUM, MAX };
 // is acc + reduction (fused tile_as VJP + accumulation).
 void launch_reduce(gadcu_ctx* ctx, gadcu_dtype dt, RedOp op, const void* in, void* out, uint64_t inner, uint64_t reduce,
                    uint64_t outer, const void* acc);
+// The cut of an inner == 1 reduction (splits per segment, elements per chunk) and its second stage, for the lane-program
+// kernel that reduces a deferred value in the same order without materialising it (batched.cu: lazy_reduce).
+void reduce_contig_plan(gadcu_ctx* ctx, gadcu_dtype dt, uint64_t reduce, uint64_t outer, uint64_t* splits, uint64_t* chunk);
+void launch_reduce_partials(gadcu_ctx* ctx, gadcu_dtype dt, RedOp op, const void* partials, void* out, uint64_t splits, uint64_t outer);
 // out[0] = sum_i a[i]*b[i]; b_bcast: b is one element.  (af::dot(flat, flat), array.rs:119-126)
 void launch_dot(gadcu_ctx* ctx, gadcu_dtype dt, const void* a, const void* b, bool a_bcast, bool b_bcast, void* out,
                 uint64_t n);

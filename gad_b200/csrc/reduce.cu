@@ -205,6 +205,24 @@ __global__ void __launch_bounds__(kThreads) random_kernel(T* out, uint64_t n, ui
   }
 }
 
+// How a contiguous segment of `reduce` elements is cut (the documented order above depends on nothing else): also used
+// by the lane-program kernel that reduces a deferred elementwise value without writing it (batched.cu), which has to
+// produce the same bits as this file's kernel run over the materialised value.
+void contig_plan(int sm_count, int V, uint64_t reduce, uint64_t outer, uint64_t& splits, uint64_t& chunk) {
+  const uint64_t target_blocks = uint64_t(sm_count) * 8;
+  splits = 1;
+  if (outer < target_blocks) {
+    splits = target_blocks / outer;
+    const uint64_t max_splits = (reduce + 8191) / 8192;  // at least 8192 elements per chunk
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+  }
+  chunk = (reduce + splits - 1) / splits;
+  chunk = (chunk + V - 1) / V * V;
+  splits = reduce == 0 ? 1 : (reduce + chunk - 1) / chunk;
+}
+
 template <class T, RedOp OP>
 void reduce_typed(gadcu_ctx* ctx, const T* in, const T* in2, bool dot, T* out, uint64_t inner, uint64_t reduce, uint64_t outer,
                   const T* acc) {
@@ -214,17 +232,8 @@ void reduce_typed(gadcu_ctx* ctx, const T* in, const T* in2, bool dot, T* out, u
     constexpr int V = VecT<T>::N;
     const bool vec = (reduce % V == 0) && (reinterpret_cast<uintptr_t>(in) % 16 == 0) &&
                      (!dot || reinterpret_cast<uintptr_t>(in2) % 16 == 0);
-    uint64_t splits = 1;
-    if (outer < target_blocks) {
-      splits = target_blocks / outer;
-      const uint64_t max_splits = (reduce + 8191) / 8192;  // at least 8192 elements per chunk
-      if (splits > max_splits) splits = max_splits;
-      if (splits < 1) splits = 1;
-      if (splits > 65535) splits = 65535;
-    }
-    uint64_t chunk = (reduce + splits - 1) / splits;
-    chunk = (chunk + V - 1) / V * V;
-    splits = reduce == 0 ? 1 : (reduce + chunk - 1) / chunk;
+    uint64_t splits, chunk;
+    contig_plan(ctx->sm_count, V, reduce, outer, splits, chunk);
     if (outer > 65535) {
       // fold: a segment per blockIdx.y is limited to 65535; process in slabs
       for (uint64_t o0 = 0; o0 < outer; o0 += 65535) {
@@ -297,6 +306,22 @@ void launch_reduce(gadcu_ctx* ctx, gadcu_dtype dt, RedOp op, const void* in, voi
     if (op == RedOp::SUM) reduce_typed<double, RedOp::SUM>(ctx, (const double*)in, nullptr, false, (double*)out, inner, reduce, outer, (const double*)acc);
     else reduce_typed<double, RedOp::MAX>(ctx, (const double*)in, nullptr, false, (double*)out, inner, reduce, outer, (const double*)acc);
   }
+}
+
+void reduce_contig_plan(gadcu_ctx* ctx, gadcu_dtype dt, uint64_t reduce, uint64_t outer, uint64_t* splits, uint64_t* chunk) {
+  contig_plan(ctx->sm_count, dt == GADCU_F32 ? 4 : 2, reduce, outer, *splits, *chunk);
+}
+
+// second stage of a split contiguous reduction: out[seg] = the segment's `splits` partials combined in chunk order
+void launch_reduce_partials(gadcu_ctx* ctx, gadcu_dtype dt, RedOp op, const void* partials, void* out, uint64_t splits, uint64_t outer) {
+  ProfileScope prof_scope(ctx, PROF_REDUCE);
+  dim3 grid2(1, (unsigned)outer);
+#define LAUNCH_STAGE2(T, OP) \
+  reduce_contig_kernel<T, OP, false, false><<<grid2, kThreads, 0, ctx->stream>>>((const T*)partials, nullptr, (T*)out, nullptr, splits, splits)
+  if (dt == GADCU_F32) { if (op == RedOp::SUM) LAUNCH_STAGE2(float, RedOp::SUM); else LAUNCH_STAGE2(float, RedOp::MAX); }
+  else { if (op == RedOp::SUM) LAUNCH_STAGE2(double, RedOp::SUM); else LAUNCH_STAGE2(double, RedOp::MAX); }
+#undef LAUNCH_STAGE2
+  ctx->count_launch();
 }
 
 void launch_dot(gadcu_ctx* ctx, gadcu_dtype dt, const void* a, const void* b, bool a_bcast, bool b_bcast, void* out, uint64_t n) {

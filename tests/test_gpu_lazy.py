@@ -52,8 +52,55 @@ def test_deferred_unary_forward_and_vjp(lazy_ctx, oracle, op, dt):
     assert_close(lazy["grads"][0], plain["grads"][0], 0)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,rd", [((1_000_003,), (1,)), ((4 * 1184 * 8192 // 16 + 4,), (1,)), ((40_000,), (1,)), ((4096, 37), (1, 37)),
+                                      ((4099, 5), (1, 5)), ((128, 64, 3), (1, 1, 3)), ((128, 64, 3), (1, 1, 1)), ((6, 1), (1, 1))], ids=str)
+@pytest.mark.parametrize("op", ["sum_as", "max_as"])
+def test_reduction_of_a_deferred_value_is_fused_and_bit_identical(lazy_ctx, op, shape, rd, dt):
+    """sum_as / max_as over the leading axes of a value that is still a deferred chain: one kernel computes the chain and
+    reduces it in reduce.cu's own order (same cut into chunks, same order inside a chunk) — the bits are those of
+    materialise-then-reduce, the value itself is never written (no launch of the elementwise region)."""
+    x, y = rand(shape, 5, -1.0, 1.0, dt), rand(shape, 6, 0.5, 2.0, dt)
+    dx, dy = lazy_ctx.array(x), lazy_ctx.array(y)
+
+    def chain(ev):
+        a, b = ev.constant(dx), ev.constant(dy)
+        return getattr(ev, op)(ev.add(ev.mul(ev.exp(a), ev.log(b)), a), rd)
+
+    ev = gb.Eval(lazy_ctx)
+    chain(ev).data().numpy()  # compile
+    l0 = lazy_ctx.launches()
+    fused = chain(ev).data()
+    launched = lazy_ctx.launches() - l0
+    lazy_ctx.set_fusion(False)
+    plain = chain(gb.Eval(lazy_ctx)).data().numpy()
+    lazy_ctx.set_fusion(True)
+    got = fused.numpy()
+    assert got.dtype == dt and got.shape == plain.shape
+    assert np.array_equal(got, plain), np.max(np.abs(got - plain))
+    assert launched <= 2, launched  # the reducing kernel (+ the second stage when a segment was cut)
+    ref = (np.exp(x.astype(np.float64)) * np.log(y.astype(np.float64)) + x).reshape(shape + (1,) * (4 - len(shape)), order="F")
+    axes = tuple(i for i in range(len(rd)) if rd[i] != shape[i])
+    want = ref.sum(axis=axes, keepdims=True) if op == "sum_as" else ref.max(axis=axes, keepdims=True)
+    scale = np.abs(ref).sum(axis=axes, keepdims=True) if op == "sum_as" else np.abs(want)
+    assert np.all(np.abs(got - want) <= 64 * np.finfo(dt).eps * scale + np.finfo(dt).tiny)
+
+
+def test_fused_reduction_leaves_the_value_usable(lazy_ctx):
+    """The reduced value stays a deferred chain: read afterwards (or consumed by a later op) it is computed then."""
+    x = rand((70_001,), 8, -1.0, 1.0)
+    ev = gb.Eval(lazy_ctx)
+    d = ev.mul(ev.exp(ev.constant(lazy_ctx.array(x))), ev.constant(lazy_ctx.array(x)))
+    s = ev.sum_as(d, (1,)).data().numpy()
+    later = ev.addc(d, 1).data().numpy().reshape(-1)
+    want = (np.exp(x) * x).astype(np.float32)
+    assert np.allclose(later, want + 1, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(d.data().numpy().reshape(-1) + np.float32(1), later)
+    assert abs(float(s.reshape(-1)[0]) - float(want.astype(np.float64).sum())) <= 64 * np.finfo(np.float32).eps * np.abs(want).sum()
+
+
 def test_one_kernel_per_region(lazy_ctx):
-    """C3: the forward is one compiled kernel + the reduction, the whole reverse sweep is one compiled kernel that
+    """C3: the forward is one compiled kernel that reduces what it computes, the whole reverse sweep is one compiled kernel that
     reads x, y and writes both gradients (the 4-pass algorithmic traffic)."""
     n = 1_000_003  # vector body + scalar tail
     x, y = rand((n,), 3, -1, 1), rand((n,), 4, 0.5, 2.0)
@@ -66,7 +113,7 @@ def test_one_kernel_per_region(lazy_ctx):
     l1 = lazy_ctx.launches()
     store = g.evaluate_gradients_once(z.gid(), 1.0)
     l2 = lazy_ctx.launches()
-    assert l1 - l0 <= 3, l1 - l0      # elementwise chain + reduction (two-stage at most)
+    assert l1 - l0 <= 2, l1 - l0      # elementwise chain and reduction in ONE kernel + the second stage over its partials
     assert l2 - l1 == 2, l2 - l1      # the seed scalar's fill + ONE kernel for the sweep
     gx, gy = store.get(vx.gid()).numpy().reshape(-1), store.get(vy.gid()).numpy().reshape(-1)
     lazy_ctx.set_fusion(False)
