@@ -4,6 +4,8 @@
 // Graph1 sweep (gradient algebra = Eval, gad/src/graph.rs:250-256) and records the GraphN sweep
 // (gradient algebra = the graph itself, graph.rs:294-300).
 #pragma once
+#include <initializer_list>
+#include <new>
 #include <functional>
 #include <map>
 #include <queue>
@@ -230,13 +232,66 @@ struct CustomVjp {
   ~CustomVjp() { if (drop && user) drop(user); }
 };
 
+// A vector whose first N elements live inside the object: a node has one or two inputs and captures at most two values
+// in all but a few ops, and a tape is recorded again every step (net_ext.rs:52) — two heap blocks per node were a third
+// of the cost of recording one.
+template <class T, unsigned N>
+class SmallVec {
+ public:
+  SmallVec() = default;
+  SmallVec(std::initializer_list<T> l) { assign(l.begin(), l.end()); }
+  SmallVec(const SmallVec& o) { assign(o.begin(), o.end()); }
+  SmallVec(SmallVec&& o) noexcept { take(std::move(o)); }
+  SmallVec(const std::vector<T>& v) { assign(v.begin(), v.end()); }
+  ~SmallVec() { destroy(); }
+  SmallVec& operator=(const SmallVec& o) { if (this != &o) { clear(); assign(o.begin(), o.end()); } return *this; }
+  SmallVec& operator=(SmallVec&& o) noexcept { if (this != &o) { destroy(); take(std::move(o)); } return *this; }
+  SmallVec& operator=(std::initializer_list<T> l) { clear(); assign(l.begin(), l.end()); return *this; }
+  SmallVec& operator=(const std::vector<T>& v) { clear(); assign(v.begin(), v.end()); return *this; }
+  void push_back(const T& v) { grow(size_ + 1); new (data() + size_) T(v); size_++; }
+  void push_back(T&& v) { grow(size_ + 1); new (data() + size_) T(std::move(v)); size_++; }
+  void clear() { for (uint32_t i = 0; i < size_; i++) data()[i].~T(); size_ = 0; }
+  size_t size() const { return size_; }
+  bool empty() const { return size_ == 0; }
+  T* data() { return heap_ ? heap_ : reinterpret_cast<T*>(inline_); }
+  const T* data() const { return heap_ ? heap_ : reinterpret_cast<const T*>(inline_); }
+  T& operator[](size_t i) { return data()[i]; }
+  const T& operator[](size_t i) const { return data()[i]; }
+  T* begin() { return data(); }
+  T* end() { return data() + size_; }
+  const T* begin() const { return data(); }
+  const T* end() const { return data() + size_; }
+
+ private:
+  template <class It> void assign(It first, It last) { for (; first != last; ++first) push_back(*first); }
+  void grow(uint32_t want) {
+    if (want <= cap_) return;
+    uint32_t cap = cap_ * 2 > want ? cap_ * 2 : want;
+    T* fresh = static_cast<T*>(::operator new(sizeof(T) * cap));
+    for (uint32_t i = 0; i < size_; i++) { new (fresh + i) T(std::move(data()[i])); data()[i].~T(); }
+    if (heap_) ::operator delete(heap_);
+    heap_ = fresh;
+    cap_ = cap;
+  }
+  void destroy() { clear(); if (heap_) { ::operator delete(heap_); heap_ = nullptr; cap_ = N; } }
+  void take(SmallVec&& o) {  // *this holds nothing
+    if (o.heap_) { heap_ = o.heap_; cap_ = o.cap_; size_ = o.size_; o.heap_ = nullptr; o.cap_ = N; o.size_ = 0; return; }
+    for (uint32_t i = 0; i < o.size_; i++) new (reinterpret_cast<T*>(inline_) + i) T(std::move(o.data()[i]));
+    size_ = o.size_;
+    o.clear();
+  }
+  T* heap_ = nullptr;
+  uint32_t size_ = 0, cap_ = N;
+  alignas(T) unsigned char inline_[sizeof(T) * N];
+};
+
 // graph.rs:46-62: inputs + update function. The update function is an op code plus the captured
 // forward values instead of a boxed closure, so the sweep can choose fused kernels per node.
 struct Node {
   Op op = Op::VARIABLE;
   bool has_update = false;
-  std::vector<Id> inputs;    // pushed on the heap after the update (index 0 = None)
-  std::vector<Value> saved;  // captured forward values (clones are O(1) handle copies)
+  SmallVec<Id, 2> inputs;    // pushed on the heap after the update (index 0 = None)
+  SmallVec<Value, 2> saved;  // captured forward values (clones are O(1) handle copies)
   double c = 0.0;
   bool c_is_int = false;
   Dim4 d;                    // op-specific dims (vdims or rdims)

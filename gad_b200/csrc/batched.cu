@@ -1916,11 +1916,14 @@ void lazy_flush(const std::vector<ArrayRef>& values) {
   }
 }
 
+std::atomic<uint32_t> g_instrs_hint{0};
+
 std::unique_ptr<GraphAlgebra> make_batched(gadcu_ctx* ctx, gadcu_dtype dt, uint64_t lanes) {
   auto prog = std::make_shared<SymProgram>();
   prog->ctx = ctx;
   prog->dtype = dt;
   prog->lanes = lanes;
+  prog->instrs.reserve(g_instrs_hint.load(std::memory_order_relaxed));  // (the last batched program's length: same tape every step)
   auto sym = std::make_shared<SymAlgebra>(ctx, prog);
   auto g = std::make_unique<GraphAlgebra>(ctx, false, sym);
   g->set_kind(GADCU_BATCHED1);
@@ -2057,6 +2060,7 @@ std::unique_ptr<Store> batched_evaluate_gradients(GraphAlgebra& g, Id id, ArrayR
   store->program_slots = sym->program()->last_slots;
   // what a re-run needs: the program and, per variable (creation order), the register of its gradient
   store->lane_program = sym->program();
+  g_instrs_hint.store(uint32_t(std::min<size_t>(sym->program()->instrs.size(), 1u << 16)), std::memory_order_relaxed);
   {
     // input slot of every variable (creation order): variables are loaded by buffer on first use
     auto prog = sym->program();

@@ -41,6 +41,9 @@ void gadcu_store::add_fused(EvalAlgebra& ev, Id id, k::EwOp op, std::initializer
 namespace gadcu {
 
 static std::atomic<uint32_t> g_arena_counter{1};
+// nodes of the tape swept last: a program records the same tape every step, so the next one starts with room for it
+// (four reallocations, each moving every node recorded so far, per 569-node tape otherwise)
+static std::atomic<uint32_t> g_tape_nodes_hint{0};
 
 GraphAlgebra::GraphAlgebra(gadcu_ctx* c, bool higher_order, std::shared_ptr<Algebra> eval)
     : Algebra(c), higher_order_(higher_order), arena_id_(g_arena_counter.fetch_add(1)),
@@ -48,6 +51,8 @@ GraphAlgebra::GraphAlgebra(gadcu_ctx* c, bool higher_order, std::shared_ptr<Alge
   if (higher_order)
     if (auto* ev = dynamic_cast<EvalAlgebra*>(eval_.get())) ev->fuse_tails = false;
   c->epoch.fetch_add(1, std::memory_order_relaxed);  // a new tape: TF32 splits cached by earlier steps expire
+  const uint32_t hint = g_tape_nodes_hint.load(std::memory_order_relaxed);
+  if (hint) nodes_.reserve(std::min<uint32_t>(hint, 1u << 16));
 }
 
 // graph.rs:94-101
@@ -655,6 +660,7 @@ std::unique_ptr<Store> GraphAlgebra::sweep(Algebra& ga, Id gid, Value gradient, 
   // from several threads, graph.rs:263-274)
   // (Graph1: gradients are data. GraphN — the data-parallel compute_gradients — too: the hook sees the data of the
   // recorded gradient value and answers with the array that replaces it in the store, as a constant)
+  g_tape_nodes_hint.store(uint32_t(nodes_.size()), std::memory_order_relaxed);
   const bool hooked = bool(final_hook_);
   std::vector<uint32_t> unhooked;
   std::vector<uint32_t>& waiting = hooked ? waiting_ : unhooked;  // by node index; only variables are counted
@@ -749,6 +755,7 @@ bool GraphAlgebra::structure_hash(uint64_t out[2], const std::function<int64_t(c
     h2 ^= h2 >> 33;
   };
   if (final_hook_ || higher_order_) return false;
+  g_tape_nodes_hint.store(uint32_t(nodes_.size()), std::memory_order_relaxed);  // (a replayed sweep never reaches sweep())
   mix(nodes_.size());
   for (const Node& n : nodes_) {
     if (n.op == Op::CUSTOM || n.custom) return false;
