@@ -219,3 +219,28 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_a_gpu():
         if not has_gpu:
             run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
             assert run.returncode == 2 and "gadcu::Error kind 8" in run.stdout, run.stdout
+
+
+def test_tape_node_container_semantics():
+    """gadcu::SmallVec (csrc/algebra.h), the inline-first container of a node's inputs and captured values: copy, move,
+    growth past the inline capacity, assignment in every direction and `Node::clear`, checked with an element type that
+    counts its constructions and destructions (tests/cpp/smallvec_test.cc; host-only, no CUDA call)."""
+    import shutil
+    import tempfile
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("no CUDA headers")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "smallvec_test")
+        res = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-fsanitize=address,undefined", "-I", os.path.join(root, "gad_b200", "csrc"),
+                              "-I", os.path.join(root, "include"), "-I", cuda_inc, os.path.join(root, "tests", "cpp", "smallvec_test.cc"), "-o", exe],
+                             capture_output=True, text=True)
+        if res.returncode != 0 and "sanitize" in res.stderr:  # (no sanitizer runtime in the image: the counting element type still checks)
+            res = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(root, "gad_b200", "csrc"), "-I", os.path.join(root, "include"),
+                                  "-I", cuda_inc, os.path.join(root, "tests", "cpp", "smallvec_test.cc"), "-o", exe], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode == 0 and run.stdout.strip().endswith("ok"), run.stdout + run.stderr
