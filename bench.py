@@ -294,13 +294,15 @@ def run_ours(args):
 
     host_ms = [0.0]
 
-    def timed(fn, steps):
+    def timed(fn, steps, drain=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
         t_host = time.perf_counter()
         for _ in range(steps):
             fn()
+        if drain is not None:
+            drain()  # (what the loop still owes — the last step's read-back — belongs to the timed region)
         host_ms[0] = (time.perf_counter() - t_host) * 1e3 / steps  # time to ISSUE a step (the device may lag behind)
         e1.record(ext)
         e1.synchronize()
@@ -341,15 +343,30 @@ def run_ours(args):
     hT.normal_(generator=torch.Generator().manual_seed(9 + rank))
     nX, nT = hX.numpy(), hT.numpy()
     # double-buffered input prefetch, as a training loop's loader does it: while step i computes, the copy stream
-    # brings step i+1's X / target rows from pinned host memory. Every timed step issues exactly one such pair of
-    # copies and reads its own loss back (which also orders step i+1 behind step i's reads of the buffers).
+    # brings step i+1's X / target rows from pinned host memory (the copy is ordered behind step i-1's reads of the
+    # buffer it overwrites: gadcu_array_upload_async). Every timed step issues exactly one such pair of copies and one
+    # device -> host copy of its own loss into pinned memory; the host picks the value up one step later
+    # (gadcu_array_download_async / gadcu_ctx_wait_download), as a training loop logs its loss, so that it can issue
+    # step i+1 while step i runs. The last step's loss is waited for inside the timed region (`drain`).
+    # GADCU_E2E_SYNC_LOSS=1: the earlier loop (item() every step: the host waits for each step before issuing the next).
     bufs = [(ctx.empty((rows, D)), ctx.empty((rows, D))) for _ in range(2)]
-    e2e_loss, e2e_i = {}, [0]
+    hloss = [torch.zeros((1,), dtype=torch.float32).pin_memory() for _ in range(2)]
+    nloss = [h.numpy() for h in hloss]
+    sync_loss = os.environ.get("GADCU_E2E_SYNC_LOSS", "0") == "1"
+    e2e_loss, e2e_i, e2e_pending = {"n": 0}, [0], [None]
 
     def prefetch(i):
         bx, bt = bufs[i % 2]
         bx.upload_async(nX)
         bt.upload_async(nT)
+
+    def collect():
+        if e2e_pending[0] is not None:
+            ticket, slot = e2e_pending[0]
+            ctx.wait_download(ticket)
+            e2e_loss["v"] = float(nloss[slot][0])
+            e2e_loss["n"] += 1
+            e2e_pending[0] = None
 
     def step_e2e():
         i = e2e_i[0]
@@ -357,16 +374,26 @@ def run_ours(args):
         prefetch(i + 1)          # next step's inputs, overlapping this step's kernels
         bx, bt = bufs[i % 2]
         out = wl.mlp_step(ctx, bx, Ws, bs, bt, comm, overlap)
-        e2e_loss["v"] = out[0].item()  # device -> host read of the step's result
+        if sync_loss:
+            e2e_loss["v"] = out[0].item()  # device -> host read of the step's result, host waits
+            e2e_loss["n"] += 1
+        else:
+            ticket = out[0].download_async(nloss[i % 2])  # queued behind this step's kernels
+            collect()                                     # the previous step's loss: on the host by now
+            e2e_pending[0] = (ticket, i % 2)
         e2e_i[0] = i + 1
 
     prefetch(0)
     for _ in range(3):
         step_e2e()
+    collect()
     e2e_steps = max(1, args.steps)
-    ms_e2e = timed(step_e2e, e2e_steps)
+    reads0 = e2e_loss["n"]
+    ms_e2e = timed(step_e2e, e2e_steps, drain=collect)
+    assert e2e_loss["n"] - reads0 == e2e_steps, "every timed step's loss must have reached the host inside the timed region"
     e2e = {"value": e2e_steps / (ms_e2e / 1000.0), "unit": "steps/s", "h2d_bytes_per_step": int(2 * rows * D * 4 * world),
-           "d2h_bytes_per_step": int(4 * world), "ms_per_step": ms_e2e / e2e_steps}
+           "d2h_bytes_per_step": int(4 * world), "ms_per_step": ms_e2e / e2e_steps, "loss": e2e_loss.get("v"),
+           "loss_read": "item() every step" if sync_loss else "async copy queued by the step, value taken one step later; all inside the timed region"}
     del bufs
 
     pk = peaks()

@@ -81,6 +81,8 @@ SIGNATURES = {
     "gadcu_array_upload": (C.c_int, [P, P, P]),
     "gadcu_array_upload_async": (C.c_int, [P, P]),
     "gadcu_ctx_wait_uploads": (C.c_int, [P]),
+    "gadcu_array_download_async": (C.c_int, [P, P, C.POINTER(C.c_uint64)]),
+    "gadcu_ctx_wait_download": (C.c_int, [P, C.c_uint64]),
     "gadcu_array_clone": (C.c_int, [P, PP]),
     "gadcu_array_retain": (C.c_int, [P]),
     "gadcu_array_release": (C.c_int, [P]),

@@ -132,6 +132,10 @@ class Context:
     def synchronize(self) -> None:
         _check(self.lib.gadcu_ctx_synchronize(self.handle))
 
+    def wait_download(self, ticket: int) -> None:
+        """Block until the download_async that returned `ticket` (and every earlier one) has landed in host memory."""
+        _check(self.lib.gadcu_ctx_wait_download(self.handle, C.c_uint64(ticket)))
+
     def wait_uploads(self) -> None:
         """The compute stream waits (on the device) for every upload_async issued so far."""
         _check(self.lib.gadcu_ctx_wait_uploads(self.handle))
@@ -292,6 +296,20 @@ class CuArray:
     def upload_async(self, pinned: np.ndarray) -> None:
         """Prefetch from pinned host memory on the copy stream; readers go after ctx.wait_uploads()."""
         _check(self.ctx.lib.gadcu_array_upload_async(self.handle, pinned.ctypes.data_as(C.c_void_p)))
+
+    def download_async(self, pinned: np.ndarray) -> int:
+        """Queue the device -> host copy of this array into `pinned` behind the work that produces it and return a ticket;
+        the bytes are there after ctx.wait_download(ticket). The host is not held up (unlike numpy() / item())."""
+        if not pinned.flags["C_CONTIGUOUS"] and not pinned.flags["F_CONTIGUOUS"]:
+            raise ValueError("download_async needs a contiguous host buffer")
+        n = 1
+        for d in self.dims():
+            n *= d
+        if pinned.nbytes < n * (4 if self.dtype == F32 else 8):
+            raise ValueError("download_async: host buffer too small")
+        t = C.c_uint64()
+        _check(self.ctx.lib.gadcu_array_download_async(self.handle, pinned.ctypes.data_as(C.c_void_p), C.byref(t)))
+        return int(t.value)
 
     def device_ptr(self) -> int:
         return int(self.ctx.lib.gadcu_array_device_ptr(self.handle) or 0)

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <deque>
 #include <cstdint>
 #include <exception>
 #include <map>
@@ -96,6 +97,8 @@ struct gadcu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t side_stream = nullptr;  // collectives / uploads
+  std::deque<std::pair<uint64_t, cudaEvent_t>> downloads;  // gadcu_array_download_async: (ticket, recorded behind the copy), oldest first
+  uint64_t download_ticket = 0;
   int sm_count = 148;
   std::shared_ptr<gadcu::Pool> pool;          // general pool
   std::shared_ptr<gadcu::Pool> capture_pool;  // non-null while capturing

@@ -241,6 +241,8 @@ gadcu_status gadcu_ctx_destroy(gadcu_ctx* ctx) {
     ctx->replay_execs.clear();
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side_stream);
+    for (auto& d : ctx->downloads) cudaEventDestroy(d.second);
+    ctx->downloads.clear();
     if (ctx->pinned_scratch) cudaFreeHost(ctx->pinned_scratch);
     if (ctx->dev_scratch) cudaFree(ctx->dev_scratch);
     if (ctx->gemm_flags) cudaFree(ctx->gemm_flags);
@@ -375,6 +377,36 @@ gadcu_status gadcu_ctx_wait_uploads(gadcu_ctx* ctx) {
     GADCU_CUDA(cudaEventRecord(ev, ctx->side_stream));
     GADCU_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
     GADCU_CUDA(cudaEventDestroy(ev));
+  });
+}
+gadcu_status gadcu_array_download_async(const gadcu_array* a, void* pinned_host, uint64_t* ticket) {
+  return guard([&] {
+    if (!a || !pinned_host || !ticket) fail(GADCU_ERR_INVALID, "download_async: null argument");
+    ArrayRef dense = materialize(ArrayRef(const_cast<gadcu_array*>(a), true));
+    gadcu_ctx* ctx = a->ctx;
+    ctx->segment_flush();
+    GADCU_CUDA(cudaMemcpyAsync(pinned_host, dense->ptr(), dense->elements() * dense->elem_size(), cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEvent_t ev;
+    GADCU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    GADCU_CUDA(cudaEventRecord(ev, ctx->stream));
+    ctx->downloads.emplace_back(++ctx->download_ticket, ev);
+    *ticket = ctx->download_ticket;
+  });
+}
+gadcu_status gadcu_ctx_wait_download(gadcu_ctx* ctx, uint64_t ticket) {
+  return guard([&] {
+    if (ticket > ctx->download_ticket) fail(GADCU_ERR_INVALID, "wait_download: no such ticket");
+    // copies complete in ticket order (one stream): the newest event not after `ticket` covers all the older ones
+    cudaEvent_t last = nullptr;
+    while (!ctx->downloads.empty() && ctx->downloads.front().first <= ticket) {
+      if (last) cudaEventDestroy(last);
+      last = ctx->downloads.front().second;
+      ctx->downloads.pop_front();
+    }
+    if (!last) return;  // retired by an earlier wait
+    const cudaError_t e = cudaEventSynchronize(last);
+    cudaEventDestroy(last);
+    if (e != cudaSuccess) fail(GADCU_ERR_CUDA, std::string("wait_download: ") + cudaGetErrorString(e));
   });
 }
 gadcu_status gadcu_array_to_host(const gadcu_array* a, void* host) {

@@ -135,6 +135,12 @@ GADCU_API gadcu_status gadcu_array_upload(gadcu_array* a, const void* pinned_hos
  * must be issued after gadcu_ctx_wait_uploads(), which makes the compute stream wait for the copies (no host sync). */
 GADCU_API gadcu_status gadcu_array_upload_async(gadcu_array* a, const void* pinned_host);
 GADCU_API gadcu_status gadcu_ctx_wait_uploads(gadcu_ctx* ctx);
+/* The read-back mirror of the prefetch: the device -> host copy of `a` into caller-owned (pinned) memory is queued on the
+ * compute stream behind the work that produces `a`, and the call returns at once with a ticket; the host looks at the bytes
+ * after gadcu_ctx_wait_download(ticket) — typically one step later, so that reading a step's loss (what a training loop logs)
+ * does not keep the host from issuing the next step. Tickets complete in order; waiting for a retired one returns at once. */
+GADCU_API gadcu_status gadcu_array_download_async(const gadcu_array* a, void* pinned_host, uint64_t* ticket);
+GADCU_API gadcu_status gadcu_ctx_wait_download(gadcu_ctx* ctx, uint64_t ticket);
 /* af::Array::clone: a NEW handle on the same device buffer, O(1) (what gad's pervasive `.clone()` costs: graph.rs:152-155,
  * net.rs:100-130 get_weights). Handles made this way are independent values: gadcu_array_add_assign on one of them
  * leaves the others' contents alone (copy-on-write). gadcu_array_retain, by contrast, adds a reference to the SAME handle. */

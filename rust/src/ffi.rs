@@ -159,11 +159,13 @@ extern "C" {
     pub fn gadcu_ctx_profile_begin(ctx: *mut gadcu_ctx) -> gadcu_status;
     pub fn gadcu_ctx_profile_end(ctx: *mut gadcu_ctx, ms_by_category4: *mut f64, count_by_category4: *mut u64) -> gadcu_status;
     pub fn gadcu_ctx_wait_uploads(ctx: *mut gadcu_ctx) -> gadcu_status;
+    pub fn gadcu_ctx_wait_download(ctx: *mut gadcu_ctx, ticket: u64) -> gadcu_status;
     // arrays
     pub fn gadcu_array_alloc(ctx: *mut gadcu_ctx, dt: c_int, dims: D, out: *mut *mut gadcu_array) -> gadcu_status;
     pub fn gadcu_array_random(ctx: *mut gadcu_ctx, dt: c_int, dims: D, seed: u64, normal: c_int, a: f64, b: f64, out: *mut *mut gadcu_array) -> gadcu_status;
     pub fn gadcu_array_upload(a: *mut gadcu_array, pinned_host: *const c_void, stream_or_null: *mut c_void) -> gadcu_status;
     pub fn gadcu_array_upload_async(a: *mut gadcu_array, pinned_host: *const c_void) -> gadcu_status;
+    pub fn gadcu_array_download_async(a: *const gadcu_array, pinned_host: *mut c_void, ticket: *mut u64) -> gadcu_status;
     pub fn gadcu_array_dtype(a: *const gadcu_array) -> c_int;
     pub fn gadcu_array_is_scalar(a: *const gadcu_array) -> c_int;
     pub fn gadcu_array_device_ptr(a: *const gadcu_array) -> *mut c_void;
