@@ -4,6 +4,9 @@
 // Graph1 sweep (gradient algebra = Eval, gad/src/graph.rs:250-256) and records the GraphN sweep
 // (gradient algebra = the graph itself, graph.rs:294-300).
 #pragma once
+#include <algorithm>
+#include <climits>
+#include <cstdint>
 #include <initializer_list>
 #include <new>
 #include <functional>
@@ -309,12 +312,40 @@ struct Node {
 
 // store.rs:60-140 — one map serves Graph1 (values carry no id) and GraphN (values carry ids).
 struct gadcu_store {
-  std::map<gadcu::Id, gadcu::Value> values;
+  mutable std::map<gadcu::Id, gadcu::Value> values;
+  // Entries a replayed batched sweep (batched.cu: sweep memo) has not turned into handles yet: (node index, register of the
+  // lane program), ascending, register -1 once the entry has moved into `values`. A 569-node tape leaves 569 entries of which
+  // its caller reads the 64 variables'; the handle of an entry is made when somebody first looks at it.
+  mutable std::vector<std::pair<uint32_t, int32_t>> deferred;
+  uint32_t deferred_arena = 0;
+  gadcu::ArrayRef (*deferred_handle)(const std::shared_ptr<void>& lane_program, int32_t reg) = nullptr;
+  int32_t* deferred_slot(gadcu::Id id) const {  // the live deferred entry of `id`, or null
+    if (deferred.empty() || id.arena != deferred_arena) return nullptr;
+    auto it = std::lower_bound(deferred.begin(), deferred.end(), std::make_pair(id.index, INT32_MIN));
+    return it != deferred.end() && it->first == id.index && it->second >= 0 ? &it->second : nullptr;
+  }
+  void realize(gadcu::Id id) const {
+    if (int32_t* reg = deferred_slot(id)) {
+      values.emplace(id, gadcu::Value(deferred_handle(lane_program, *reg)));
+      *reg = -1;
+    }
+  }
   const gadcu::Value* get(gadcu::Id id) const {
+    realize(id);
     auto it = values.find(id);
     return it == values.end() ? nullptr : &it->second;
   }
-  void insert(gadcu::Id id, gadcu::Value v) { values[id] = std::move(v); }
+  std::vector<gadcu::Id> ids() const {  // ascending
+    std::vector<gadcu::Id> out;
+    out.reserve(values.size() + deferred.size());
+    for (auto& kv : values) out.push_back(kv.first);
+    const size_t mid = out.size();
+    for (auto& d : deferred)
+      if (d.second >= 0) out.push_back(gadcu::Id{deferred_arena, d.first});
+    std::inplace_merge(out.begin(), out.begin() + long(mid), out.end());
+    return out;
+  }
+  void insert(gadcu::Id id, gadcu::Value v) { realize(id); values[id] = std::move(v); }
   // store.rs:44-55
   void add_gradient(gadcu::Algebra& graph, gadcu::Id id, const gadcu::Value& value);
   // fused: contribution = op(ins...) computed and accumulated by one kernel (Graph1 + fusion only)

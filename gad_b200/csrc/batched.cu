@@ -2012,11 +2012,14 @@ std::unique_ptr<Store> batched_evaluate_gradients(GraphAlgebra& g, Id id, ArrayR
       store = std::make_unique<Store>();
       std::vector<uint32_t> visited;
       visited.reserve(hit->store_regs.size());
-      auto hint = store->values.end();
-      for (auto& pr : hit->store_regs) {
-        hint = store->values.emplace_hint(hint, Id{id.arena, pr.first}, Value(sym_array(prog0, pr.second)));
-        visited.push_back(pr.first);
-      }
+      for (auto& pr : hit->store_regs) visited.push_back(pr.first);
+      // the entries stay (index, register) pairs until somebody looks at them (gadcu_store::realize)
+      store->deferred = std::move(copy.store_regs);
+      store->deferred_arena = id.arena;
+      store->deferred_handle = [](const std::shared_ptr<void>& program, int32_t reg) {
+        return sym_array(std::static_pointer_cast<SymProgram>(program), reg);
+      };
+      store->lane_program = prog0;
       if (once) g.consume(visited);
       g_sweeps_replayed++;
     }
@@ -2046,6 +2049,11 @@ std::unique_ptr<Store> batched_evaluate_gradients(GraphAlgebra& g, Id id, ArrayR
   std::vector<int32_t> regs;
   std::vector<Id> ids;
   for (Id vid : var_ids) {
+    if (const int32_t* reg = store->deferred_slot(vid)) {  // (a replayed sweep: no handle yet, and none needed)
+      regs.push_back(*reg);
+      ids.push_back(vid);
+      continue;
+    }
     auto it = store->values.find(vid);
     if (it != store->values.end() && it->second.data->symbolic()) {
       regs.push_back(it->second.data->sym_reg);
@@ -2054,7 +2062,14 @@ std::unique_ptr<Store> batched_evaluate_gradients(GraphAlgebra& g, Id id, ArrayR
   }
   if (!regs.empty()) {
     std::vector<ArrayRef> cols = sym->program()->run(regs);
-    for (size_t i = 0; i < ids.size(); i++) store->values[ids[i]].data = cols[i];
+    for (size_t i = 0; i < ids.size(); i++) {
+      if (int32_t* reg = store->deferred_slot(ids[i])) {
+        *reg = -1;
+        store->values.emplace(ids[i], Value(cols[i]));
+      } else {
+        store->values[ids[i]].data = cols[i];
+      }
+    }
   }
   store->program_instructions = sym->program()->last_instructions;
   store->program_slots = sym->program()->last_slots;

@@ -250,9 +250,10 @@ gadcu_status gadcu_store_get(const gadcu_store* s, uint32_t arena, uint32_t inde
   });
 }
 size_t gadcu_store_ids(const gadcu_store* s, uint32_t* out, size_t cap) {
+  std::lock_guard<std::recursive_mutex> api_lock(api_mutex());
   size_t k = 0;
-  for (auto& kv : s->values) {
-    if (k < cap) out[k] = kv.first.index;
+  for (const Id& id : s->ids()) {
+    if (k < cap) out[k] = id.index;
     k++;
   }
   return k;

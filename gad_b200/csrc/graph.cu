@@ -19,6 +19,7 @@ using namespace gadcu;
 
 // ---- store --------------------------------------------------------------------------------------
 void gadcu_store::add_gradient(Algebra& graph, Id id, const Value& value) {  // store.rs:44-55
+  realize(id);
   auto it = values.find(id);
   if (it == values.end()) {
     values.emplace(id, value);  // first contribution is stored by clone, not added to zero
@@ -29,6 +30,7 @@ void gadcu_store::add_gradient(Algebra& graph, Id id, const Value& value) {  // 
 }
 
 void gadcu_store::add_fused(EvalAlgebra& ev, Id id, k::EwOp op, std::initializer_list<const ArrayRef*> ins, double c, double c2) {
+  realize(id);
   auto it = values.find(id);
   if (it == values.end()) {
     values.emplace(id, Value(ev.fused(op, ArrayRef(), ins, c, c2)));
