@@ -383,6 +383,7 @@ gadcu_status gadcu_array_download_async(const gadcu_array* a, void* pinned_host,
   return guard([&] {
     if (!a || !pinned_host || !ticket) fail(GADCU_ERR_INVALID, "download_async: null argument");
     ArrayRef dense = materialize(ArrayRef(const_cast<gadcu_array*>(a), true));
+    if (dense->elements() != a->elements()) fail(GADCU_ERR_INVALID, "download_async on a lane value of a batched tape: read its column through gadcu_batched_force");
     gadcu_ctx* ctx = a->ctx;
     ctx->segment_flush();
     GADCU_CUDA(cudaMemcpyAsync(pinned_host, dense->ptr(), dense->elements() * dense->elem_size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -412,6 +413,8 @@ gadcu_status gadcu_ctx_wait_download(gadcu_ctx* ctx, uint64_t ticket) {
 gadcu_status gadcu_array_to_host(const gadcu_array* a, void* host) {
   return guard([&] {
     ArrayRef dense = materialize(ArrayRef(const_cast<gadcu_array*>(a), true));
+    // (a lane value of a batched tape reports the dims of ONE tape's scalar; its column has `lanes` elements)
+    if (dense->elements() != a->elements()) fail(GADCU_ERR_INVALID, "to_host on a lane value of a batched tape: read its column through gadcu_batched_force");
     a->ctx->segment_flush();
     GADCU_CUDA(cudaMemcpyAsync(host, dense->ptr(), dense->elements() * dense->elem_size(), cudaMemcpyDeviceToHost, a->ctx->stream));
     GADCU_CUDA(cudaStreamSynchronize(a->ctx->stream));

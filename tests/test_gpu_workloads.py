@@ -74,12 +74,14 @@ def test_batched_sweep_over_a_known_structure_is_replayed_not_walked(ctx, oracle
             terms.append(g.add(g.mulc(g.mul(d, d), scale), g.mul(e, e)))
         f = g.add_all(terms if root_last else terms[:-1])
         store = (g.evaluate_gradients_once if once else g.evaluate_gradients)(f.gid(), 1.0)
+        inner.append(terms[:2])
         return g, f, vs, store
 
     def grads(vs, store):
         got = [store.get(v.gid()) for v in vs]  # (None: a variable the root does not depend on)
         return np.stack([to_np(c)[:, 0, 0, 0] if c is not None else np.zeros(lanes) for c in got])
 
+    inner = []  # (two intermediate nodes of every recorded tape)
     s0 = ctx.sweep_memo_stats()
     g1, f1, v1, st1 = record(xs[0])
     s1 = ctx.sweep_memo_stats()
@@ -92,6 +94,17 @@ def test_batched_sweep_over_a_known_structure_is_replayed_not_walked(ctx, oracle
         assert np.array_equal(grads(vs, st), ograd)
     assert st1.ids() == st2.ids()
     assert len(st2.ids()) == g2.num_nodes()
+    # entries nobody asked the sweep for (the root's own gradient, an intermediate node's) are there when read, in the
+    # replayed store as in the walked one, and reading them does not change what the store lists
+    for g, st, f, terms in ((g1, st1, f1, inner[0]), (g2, st2, f2, inner[1])):
+        column = lambda entry: to_np(g.force(gb.Value(entry)))[:, 0, 0, 0]  # (a lane value is read through gadcu_batched_force)
+        assert np.array_equal(column(st.get(f.gid())), np.ones(lanes))
+        for t in terms:
+            assert np.array_equal(column(st.get(t.gid())), np.ones(lanes))  # d(sum of terms)/d(term)
+        with pytest.raises(gb.InvalidError):
+            st.get(terms[0].gid()).numpy()  # its dims are one tape's scalar: the column does not fit a host buffer sized by them
+        assert st.get(gb.GradientId(f.gid().arena, g1.num_nodes() + 5)) is None
+    assert st1.ids() == st2.ids() and len(st2.ids()) == g2.num_nodes()
     assert st2.program_stats() == st1.program_stats()
     # the replayed sweep consumed the tape like the walked one: a second sweep finds the root without its update
     for g, f in ((g1, f1), (g2, f2)):
