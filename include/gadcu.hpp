@@ -91,6 +91,7 @@ class Context {
   void set_gemm_epilogue(bool enable) { check(gadcu_ctx_set_gemm_epilogue(h_, enable)); }
   void set_auto_replay(bool enable) { check(gadcu_ctx_set_auto_replay(h_, enable)); }  // graphs keyed by the recorded kernel sequence
   void flush() { check(gadcu_ctx_flush(h_)); }
+  void wait_download(uint64_t ticket) { check(gadcu_ctx_wait_download(h_, ticket)); }  // see Array::download_async
   uint64_t launches() {
     uint64_t a, b, c;
     check(gadcu_ctx_memory_stats(h_, &a, &b, &c));
@@ -142,6 +143,13 @@ class Array {
     std::vector<T> out(dims().elements());
     check(gadcu_array_to_host(h_, out.data()));
     return out;
+  }
+  // Queue the device -> host copy of this array into caller-owned (pinned) memory of dims().elements() values behind the
+  // work that produces it; returns a ticket for Context::wait_download. The host is not held up (host() / item() are).
+  uint64_t download_async(T* pinned) const {
+    uint64_t ticket = 0;
+    check(gadcu_array_download_async(h_, pinned, &ticket));
+    return ticket;
   }
   T item() const {  // a one-element array or a device scalar (`dot`, `as_scalar`: array.rs:106-126); synchronises
     double v = 0;

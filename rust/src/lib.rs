@@ -119,6 +119,18 @@ impl<T: CuFloat> CuArray<T> {
         assert_eq!(out.len() as u64, self.dims().elements());
         unsafe { gadcu_array_to_host(self.h, out.as_mut_ptr() as *mut _); }
     }
+    /// Queue the device -> host copy into `out` (pinned memory that outlives the copy) behind the work that produces this
+    /// array and return a ticket; the bytes are there after `wait_download(ticket)`. Unlike `host`, the caller is not held
+    /// up: a training loop reads step i's loss while step i + 1 is already issued.
+    ///
+    /// # Safety
+    /// `out` must stay valid and untouched until `wait_download` has returned for the ticket.
+    pub unsafe fn download_async(&self, out: *mut T) -> u64 {
+        let mut ticket = 0u64;
+        let st = gadcu_array_download_async(self.h, out as *mut _, &mut ticket);
+        assert_eq!(st, GADCU_OK, "{}", last_error());
+        ticket
+    }
     fn from_raw(h: *mut gadcu_array) -> Self { CuArray { h, _t: PhantomData } }
     fn from_value(v: gadcu_value) -> Self { CuArray { h: v.data, _t: PhantomData } }
     fn as_value(&self) -> gadcu_value { gadcu_value { data: self.h, arena: 0, index: 0 } }
@@ -608,6 +620,17 @@ impl CuGraphN {
 pub fn set_gemm_epilogue(mode: i32) { unsafe { gadcu_ctx_set_gemm_epilogue(backend().ctx, mode); } }
 pub fn set_auto_replay(on: bool) { unsafe { gadcu_ctx_set_auto_replay(backend().ctx, on as i32); } }
 pub fn flush() { unsafe { gadcu_ctx_flush(backend().ctx); } }
+/// Block until the `CuArray::download_async` that returned `ticket` (and every earlier one) has landed in host memory.
+pub fn wait_download(ticket: u64) {
+    let st = unsafe { gadcu_ctx_wait_download(backend().ctx, ticket) };
+    assert_eq!(st, GADCU_OK, "{}", last_error());
+}
+/// Batched sweeps (replayed from the structure table, walked node by node, structures held) since process start.
+pub fn sweep_memo_stats() -> (u64, u64, u64) {
+    let (mut a, mut b, mut c) = (0u64, 0u64, 0u64);
+    unsafe { gadcu_batched_sweep_memo_stats(&mut a, &mut b, &mut c); }
+    (a, b, c)
+}
 
 /// One communicator per rank (one process per GPU); the unique id travels through whatever launched the ranks.
 pub struct CuComm { h: *mut gadcu_comm }
