@@ -732,6 +732,75 @@ std::string gen_source(const SymProgram& P, const JitPlan& J, const std::unorder
     const std::string td = "p.td[" + std::to_string(J.red_td) + "]", tdc = "p.td[" + std::to_string(J.red_td + 1) + "]",
                       tds = "p.td[" + std::to_string(J.red_td + 2) + "]";
     o << (J.red == 1 ? "#define COMB(a, b) ((a) + (b))\n#define IDENT T(0)\n" : "#define COMB(a, b) ((b) > (a) ? (b) : (a))\n") << (J.red == 1 ? "" : f32 ? "#define IDENT (-__int_as_float(0x7f800000))\n" : "#define IDENT (-__longlong_as_double(0x7ff0000000000000ll))\n");
+    if (J.ring) {
+      // ring-fed variant of the same walk: a producer warp streams the chunk's tiles of 256 vectors per dense input through a
+      // shared-memory ring (cp.async.bulk + full / empty mbarriers, as in the ring-fed region skeleton below) and runs
+      // ahead; computing thread t takes vector t of every tile — the very vectors, in the very order, of the register-fed
+      // walk (vlo + t, + 256, ...), so the accumulators see the same additions. Measured on the C3 forward (64 Mi f32, one
+      // call, same box): register-fed 0.101 ms, ring of 4 / 8 / 16 tiles 0.121 / 0.118 / 0.116 ms — with 256-thread blocks
+      // the tiles are 4 KB and every block pays its own barrier set-up for ~56 tiles; OFF unless GADCU_REDUCE_RING says so.
+      const int D = J.ring, ND = int(J.dense.size());
+      int logd = 0;
+      while ((1 << logd) < D) logd++;
+      o << "#define TILE_BYTES 4096u\n";
+      o << "__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {\n  unsigned done;\n  do {\n"
+           "    asm volatile(\"{\\n.reg .pred p;\\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\\nselp.u32 %0, 1, 0, p;\\n}\" : \"=r\"(done) : \"r\"(bar), \"r\"(parity) : \"memory\");\n"
+           "  } while (!done);\n}\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(288" << (J.stage_blocks ? ", " + std::to_string(J.stage_blocks) : std::string()) << ") lane_program(const P p) {\n";
+      o << "  extern __shared__ __align__(128) unsigned char smem[];\n  __shared__ T warp_part[8];\n";
+      o << "  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem), bfull = sbase + " << D << "u * TILE_BYTES, bempty = bfull + " << 8 * D << "u;\n";
+      o << "  if (threadIdx.x == 0) {\n    for (unsigned s = 0; s < " << D << "u; s++) {\n"
+           "      asm volatile(\"mbarrier.init.shared::cta.b64 [%0], %1;\" ::\"r\"(bfull + 8 * s), \"r\"(1u));\n"
+           "      asm volatile(\"mbarrier.init.shared::cta.b64 [%0], %1;\" ::\"r\"(bempty + 8 * s), \"r\"(8u));\n    }\n"
+           "    asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n"
+           "    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n  }\n  __syncthreads();\n";
+      o << "  const u64 reduce = " << td << ", chunk = " << tdc << ", splits = " << tds << ";\n";
+      o << "  const u64 seg = blockIdx.x / splits, split = blockIdx.x % splits;\n";
+      o << "  const u64 lo = split * chunk;\n  u64 hi = lo + chunk;\n  if (hi > reduce) hi = reduce;\n  if (hi < lo) hi = lo;\n";
+      o << "  const u64 vbase = seg * reduce / " << J.V << ", vlo = lo / " << J.V << ", vhi = hi / " << J.V << ";\n";
+      o << "  const u64 tiles = (vhi - vlo + 255ull) / 256ull;\n";
+      o << "  if (threadIdx.x >= 256) {\n    if (threadIdx.x == 256) {\n      unsigned q = 0;\n      for (u64 t = 0; t < tiles; t++) {\n"
+           "        const u64 first = vlo + t * 256ull;\n        const u64 left = vhi - first;\n"
+           "        const unsigned bytes = (unsigned)(left < 256ull ? left : 256ull) * 16u;\n";
+      for (int j = 0; j < ND; j++) {
+        o << "        {\n          const unsigned s = q & " << D - 1 << "u, ph = (q >> " << logd << ") & 1u;\n"
+             "          mbar_wait(bempty + 8 * s, ph ^ 1u);\n"
+             "          asm volatile(\"mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\" ::\"r\"(bfull + 8 * s), \"r\"(bytes) : \"memory\");\n"
+             "          asm volatile(\"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\" ::\"r\"(sbase + s * TILE_BYTES), "
+             "\"l\"(reinterpret_cast<const TV*>(p.in[" << J.dense[size_t(j)].second << "]) + vbase + first), \"r\"(bytes), \"r\"(bfull + 8 * s) : \"memory\");\n"
+             "          q++;\n        }\n";
+      }
+      o << "      }\n    }\n    return;\n  }\n";
+      for (auto& d : J.uniform) o << "  const T " << reg_name(d.first) << " = p.in[" << d.second << "][0];\n";
+      for (int l = 0; l < J.V; l++) o << "  T acc" << l << " = IDENT;\n";
+      o << "  unsigned q = 0;\n  for (u64 t = 0; t < tiles; t++) {\n    const u64 vi = vlo + t * 256ull + threadIdx.x;\n";
+      for (int j = 0; j < ND; j++) {
+        o << "    TV v" << J.local.at(J.dense[size_t(j)].first) << ";\n    {\n      const unsigned s = q & " << D - 1 << "u;\n"
+             "      mbar_wait(bfull + 8 * s, (q >> " << logd << ") & 1u);\n"
+             "      v" << J.local.at(J.dense[size_t(j)].first) << " = *reinterpret_cast<const TV*>(smem + s * TILE_BYTES + threadIdx.x * 16u);\n"
+             "      __syncwarp();\n"
+             "      if ((threadIdx.x & 31) == 0) asm volatile(\"mbarrier.arrive.shared::cta.b64 _, [%0];\" ::\"r\"(bempty + 8 * s) : \"memory\");\n"
+             "      q++;\n    }\n";
+      }
+      o << "    if (vi < vhi) {\n      const u64 gi = vbase + vi;\n";
+      for (size_t k = 0; k < J.col.size(); k++)
+        o << "      const T " << reg_name(J.col[k].first) << " = p.in[" << J.col[k].second << "][" << col_index(k, "gi * " + std::to_string(J.V)) << "];\n";
+      for (int l = 0; l < J.V; l++) {
+        o << "      T y" << l << ";\n      body(p, gi * " << J.V << " + " << l;
+        for (auto& d : J.dense) o << ", v" << J.local.at(d.first) << lanes4[l];
+        for (auto& d : J.uniform) o << ", " << reg_name(d.first);
+        for (auto& d : J.col) o << ", " << reg_name(d.first);
+        o << ", y" << l << ");\n";
+      }
+      for (int l = 0; l < J.V; l++) o << "      acc" << l << " = COMB(acc" << l << ", y" << l << ");\n";
+      o << "    }\n  }\n  T v = acc0;\n";
+      for (int l = 1; l < J.V; l++) o << "  v = COMB(v, acc" << l << ");\n";
+      o << "#pragma unroll\n  for (int off = 16; off > 0; off >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, v, off); v = COMB(v, w); }\n";
+      o << "  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;\n  asm volatile(\"bar.sync 1, 256;\" ::: \"memory\");\n";
+      o << "  if (threadIdx.x == 0) {\n    T r = warp_part[0];\n#pragma unroll\n    for (int w = 1; w < 8; w++) r = COMB(r, warp_part[w]);\n"
+           "    p.out[0][seg * splits + split] = r;\n  }\n}\n";
+      return o.str();
+    }
     o << "extern \"C\" __global__ void __launch_bounds__(256" << (J.stage_blocks ? ", " + std::to_string(J.stage_blocks) : std::string()) << ") lane_program(const P p) {\n";
     o << "  __shared__ T warp_part[8];\n";
     o << "  const u64 reduce = " << td << ", chunk = " << tdc << ", splits = " << tds << ";\n";
@@ -1063,6 +1132,13 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo, cons
     J.U = J.V == 1 ? 1 : (J.dense.size() <= 4 ? red_unroll : 1);  // loads in flight per thread (see gen_source)
     J.block = 256;
     J.red = red->op == k::RedOp::SUM ? 1 : 2;
+    static const int red_ring = [] { const char* e = getenv("GADCU_REDUCE_RING"); return e ? atoi(e) : 0; }();
+    static const uint64_t red_ring_min = [] { const char* e = getenv("GADCU_REDUCE_RING_MIN"); return e ? uint64_t(atoll(e)) : (1ull << 22); }();
+    if (red_ring > 0 && J.V == vmax && !J.dense.empty() && J.dense.size() <= 4 && lanes >= red_ring_min) {
+      J.ring = red_ring >= 2 ? red_ring : 8;  // slots of one 4 KB tile, shared by the inputs in turn
+      J.smem_bytes = size_t(J.ring) * 4096 + size_t(J.ring) * 16;
+      J.U = 1;
+    }
     J.red_td = J.tile_d0.size();
     J.tile_d0.push_back(red->reduce);
     J.tile_d0.push_back(red->chunk);
@@ -1258,7 +1334,7 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo, cons
     // reduce.cu cuts a long segment into 8 chunks per SM: compiled for 8 resident blocks (32 registers) they all run at
     // once; if the chain does not fit that budget, whatever the compiler needs (the chunks then take two rounds)
     static const int want = [] { const char* e = getenv("GADCU_REDUCE_MINBLOCKS"); return e ? atoi(e) : 8; }();
-    const std::vector<int> candidates = want > 0 ? std::vector<int>{want, 0} : std::vector<int>{0};
+    const std::vector<int> candidates = J.ring ? std::vector<int>{4, 3, 0} : want > 0 ? std::vector<int>{want, 0} : std::vector<int>{0};
     for (size_t c = 0; c < candidates.size(); c++) {
       J.stage_blocks = candidates[c];
       kernel = build(key + "|b" + std::to_string(J.stage_blocks));
@@ -1319,7 +1395,7 @@ std::vector<ArrayRef> SymProgram::run_jit(const std::vector<int32_t>& todo, cons
     if (params.size() * 8 > kMaxParamBytes) return {};
     ProfileScope prof_scope(ctx, PROF_REDUCE);
     void* args[] = {params.data()};
-    jit::launch(ctx, kernel, unsigned(red->splits * red->outer), 256u, args, 0);
+    jit::launch(ctx, kernel, unsigned(red->splits * red->outer), J.ring ? 288u : 256u, args, J.smem_bytes);
     if (red_done) *red_done = true;
     return {};
   }
