@@ -1,0 +1,28 @@
+"""GPU: gad/tests/net.rs replayed through the C++ mirror of gad's network layer (include/gadcu_net.hpp -> gadcu.hpp -> C ABI
+-> device backend): a hand-written Net and input.using(weight).map(matmul_nn) trained to the identity with
+apply_gradient_step, weights through the reference's checkpoint bytes, evaluate / check, one two-example gradient step
+against its closed form, copy-on-write weight snapshots. The program is examples/net_cpp.cc; it exits 0 when every
+expectation holds. (The same header is checked over the CPU oracle's tape in tests/test_net_cpp.py; this file sorts last
+so the kernels' parity tests are not held up behind a host-language mirror.)"""
+import os
+import shutil
+import subprocess
+import tempfile
+
+import pytest
+
+from test_net_cpp import build_device_example
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_net_tests_through_the_cpp_mirror():
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "net_cpp")
+        res = build_device_example(exe)
+        assert res.returncode == 0, res.stderr
+        run = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+        assert run.returncode == 0, run.stdout + run.stderr
+        assert "all net tests passed" in run.stdout
