@@ -5,8 +5,16 @@
 // over a two-example batch against its closed form, and a weight snapshot that must survive the update (copy-on-write).
 // The same header is checked over the CPU oracle's tape without a GPU in tests/cpp/net_test.cc. Exit code 0 = all passed.
 //   g++ -std=c++17 -Iinclude examples/net_cpp.cc -Lgad_b200/lib -lgadcu -Wl,-rpath,$PWD/gad_b200/lib -o examples/net_cpp
+// `net_cpp dp <rank> <nranks> <id file>` is one rank of the data-parallel form of the step (one process per GPU, device =
+// rank; rank 0 writes the communicator's id to the file, the others wait for it): the examples of a batch split over the
+// ranks, update and loss summed — against the same steps taken by this process alone on the whole batch.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <thread>
 
 #include "gadcu_net.hpp"
 
@@ -140,8 +148,50 @@ static void test_gradient_step_closed_form(Context& ctx) {
   EXPECT(throws(ErrorKind::MissingGradient, [&] { train.read_weight_gradients(r.second, store); }));
 }
 
-int main() {
+// gadcu::Comm + the data-parallel apply_gradient_step: uneven shares (5 examples), a rank without examples (1 example)
+static int run_dp_rank(int rank, int nranks, const std::string& id_file) {
+  Context ctx(rank);
+  std::vector<uint8_t> id(128);
+  if (rank == 0) {
+    id = Comm::unique_id();
+    std::ofstream(id_file + ".tmp", std::ios::binary).write(reinterpret_cast<const char*>(id.data()), 128);
+    std::rename((id_file + ".tmp").c_str(), id_file.c_str());
+  } else {
+    for (int tries = 0;; tries++) {
+      std::ifstream in(id_file, std::ios::binary);
+      if (in && in.read(reinterpret_cast<char*>(id.data()), 128)) break;
+      if (tries > 600) { std::printf("rank %d: no communicator id after 60 s\n", rank); return 3; }
+      std::this_thread::sleep_for(std::chrono::milliseconds(100));
+    }
+  }
+  Comm comm(ctx, nranks, rank, id);
+  const std::vector<float> t2{0.5f, 0, 1, -1, 2, 0, 0, 1, 1}, x3{0, 1, 0, 2, 0, -1, 1, 1, 0.5f};
+  auto example = [&](const std::vector<float>& x, const std::vector<float>& t) { return std::make_pair(mat(ctx, x), mat(ctx, t)); };
+  for (size_t batch_size : {size_t(5), size_t(1)}) {
+    auto together = make_net(mat(ctx, kW0)).add_square_loss<A>();  // stepped over the ranks
+    auto alone = make_net(mat(ctx, kW0)).add_square_loss<A>();     // stepped by this process on the whole batch
+    std::vector<decltype(together)::Input> batch{example(kA, kI), example(kI, t2), example(x3, kI), example(kA, t2), example(x3, t2)};
+    batch.resize(batch_size, example(kA, kI));
+    for (int step = 0; step < 5; step++) {
+      const float l_dp = apply_gradient_step(together, ctx, -0.01f, batch, comm);
+      const float l_one = apply_gradient_step(alone, ctx, -0.01f, batch);
+      EXPECT(std::fabs(l_dp - l_one) <= 1e-5f * std::fabs(l_one));
+    }
+    EXPECT(close(together.get_weights().second, alone.get_weights().second.host(), 1e-5f));
+    EXPECT(!close(together.get_weights().second, kW0, 1e-3f));  // (it did move)
+  }
+  // a plain in-place sum: every rank contributes rank + 1
+  A v = A::from_host(ctx, std::vector<float>(9, float(rank + 1)), Dim4{3, 3});
+  comm.allreduce_sum<float>({&v});
+  EXPECT(close(v, std::vector<float>(9, float(nranks * (nranks + 1) / 2)), 0.0f));
+  ctx.synchronize();
+  std::printf(failures ? "rank %d: %d expectation(s) failed\n" : "rank %d: data-parallel net steps ok (%d failures)\n", rank, failures);
+  return failures ? 1 : 0;
+}
+
+int main(int argc, char** argv) {
   try {
+    if (argc == 5 && !std::strcmp(argv[1], "dp")) return run_dp_rank(std::atoi(argv[2]), std::atoi(argv[3]), argv[4]);
     Context ctx(0);
     train_to_identity(ctx, TestNet(Dim4{3, 3}, mat(ctx, kW0)).add_square_loss<A>(), TestNet(Dim4{3, 3}, mat(ctx, kI)));
     train_to_identity(ctx, make_net(mat(ctx, kW0)).add_square_loss<A>(), make_net(mat(ctx, kI)));

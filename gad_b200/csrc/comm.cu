@@ -849,7 +849,7 @@ gadcu_status gadcu_evaluate_gradients_dp_with(gadcu_algebra* g, uint32_t arena, 
     try {
       store = graph->evaluate_gradients(Id{arena, index}, ArrayRef(seed, true), once != 0);
     } catch (...) {
-      comm->deferred.clear();
+      if (comm) comm->deferred.clear();  // (comm may be NULL: the one-process form of the call)
       try { finish(); } catch (...) {}
       throw;
     }

@@ -18,6 +18,8 @@
 //   compute_gradients             graph.rs:307-318        GraphN::compute_gradients(id, seed)
 //   GradientReader::read          store.rs:27-29          Store<T>::get(id) -> std::optional (absent is not zero)
 //   WeightOps                     net.rs:161-180          Array<T>::{add_assign, scale}
+//   (none: the reference is one process)                  gadcu::Comm + Graph1::evaluate_gradients_dp / GraphN::compute_gradients_dp:
+//                                                         the batch split over the GPUs of a box, gradients summed over the ranks
 //
 // `Err(Error::X)` in the reference is `throw gadcu::Error{X}` here; nothing else changes meaning. There is no CPU
 // fallback: constructing a Context without a B200 throws Error{Cuda}.
@@ -291,6 +293,45 @@ class Store {
   std::shared_ptr<gadcu_store> s_;
 };
 
+// Data parallelism over the batch dimension (gadcu.h "data parallelism"; new — the reference is single-process): one process
+// per GPU, every rank builds a Comm from the same 128-byte id (rank 0 makes it with Comm::unique_id() and hands it to the
+// others by whatever channel the host program has). apply_gradient_step sums per-example gradients (net_ext.rs:62-65), so
+// sharding the batch and summing the weight gradients over the ranks reproduces it up to the order of the sum.
+class Comm {
+ public:
+  static std::vector<uint8_t> unique_id() {
+    std::vector<uint8_t> id(128);
+    check(gadcu_comm_unique_id(id.data()));
+    return id;
+  }
+  Comm(Context& ctx, int nranks, int rank, const std::vector<uint8_t>& id) : nranks_(nranks), rank_(rank) {
+    if (id.size() != 128) throw Error(ErrorKind::Lengths, "Comm: the unique id is 128 bytes");
+    check(gadcu_comm_init(ctx.handle(), nranks, rank, id.data(), &h_));
+  }
+  ~Comm() { if (h_) gadcu_comm_destroy(h_); }
+  Comm(const Comm&) = delete;
+  Comm& operator=(const Comm&) = delete;
+  gadcu_comm* handle() const { return h_; }
+  int nranks() const { return nranks_; }
+  int rank() const { return rank_; }
+  // in-place sum over the ranks; the async form runs on the communicator's stream behind what the compute stream has
+  // been given so far, and join() makes the compute stream wait for it (the host is never held up)
+  template <class T> void allreduce_sum(const std::vector<Array<T>*>& arrays) { check(gadcu_comm_allreduce_sum(h_, handles(arrays).data(), arrays.size())); }
+  template <class T> void allreduce_sum_async(const std::vector<Array<T>*>& arrays) {
+    check(gadcu_comm_allreduce_sum_async(h_, handles(arrays).data(), arrays.size()));
+  }
+  void join() { check(gadcu_comm_join(h_)); }
+
+ private:
+  template <class T> static std::vector<gadcu_array*> handles(const std::vector<Array<T>*>& arrays) {
+    std::vector<gadcu_array*> h;
+    for (const Array<T>* a : arrays) h.push_back(a->handle());
+    return h;
+  }
+  gadcu_comm* h_ = nullptr;
+  int nranks_, rank_;
+};
+
 // One of gad's default algebras over device arrays; the SAME member functions serve Eval, Graph1 and GraphN, as one
 // generic gad program is instantiated with different algebras (arrayfire.rs:39-61).
 class Algebra {
@@ -477,6 +518,20 @@ class Graph1 : public Algebra {
   template <class T> Store<T> evaluate_gradients_once(Id id, const Array<T>& seed) { return sweep(id, seed, 1); }        // graph.rs:277-290
   template <class T, class = std::enable_if_t<std::is_arithmetic<T>::value>>
   Store<T> evaluate_gradients_once(Id id, T seed) { return sweep(id, Array<T>::scalar(*ctx_, seed), 1); }  // scalar roots (`as_scalar`, `dot`)
+  // The sweep of one batch shard: every variable's gradient is summed over the ranks as soon as the sweep has completed it,
+  // overlapping the rest of the sweep (gadcu_evaluate_gradients_dp); `also` — e.g. the step's loss — joins the same exchange.
+  // With one rank it IS evaluate_gradients[_once].
+  template <class T> Store<T> evaluate_gradients_dp(Id id, const Array<T>& seed, Comm& comm, bool once = true, const std::vector<Array<T>*>& also = {}) {
+    std::vector<gadcu_array*> extra;
+    for (const Array<T>* a : also) extra.push_back(a->handle());
+    gadcu_store* s = nullptr;
+    check(gadcu_evaluate_gradients_dp_with(h_, id.arena, id.index, seed.handle(), once ? 1 : 0, comm.handle(), extra.data(), extra.size(), &s));
+    return Store<T>(s);
+  }
+  template <class T, class = std::enable_if_t<std::is_arithmetic<T>::value>>
+  Store<T> evaluate_gradients_dp(Id id, T seed, Comm& comm, bool once = true, const std::vector<Array<T>*>& also = {}) {
+    return evaluate_gradients_dp(id, Array<T>::scalar(*ctx_, seed), comm, once, also);
+  }
 
  private:
   template <class T> Store<T> sweep(Id id, const Array<T>& seed, int once) const {
@@ -495,6 +550,13 @@ class GraphN : public Algebra {
     const gadcu_value v = seed.c();
     gadcu_store* s = nullptr;
     check(gadcu_compute_gradients(h_, id.arena, id.index, &v, &s));
+    return Store<T>(s);
+  }
+  // of one batch shard: each gradient is summed over the ranks when the sweep completes it and returned as a constant
+  template <class T> Store<T> compute_gradients_dp(Id id, const Value<T>& seed, Comm& comm) {
+    const gadcu_value v = seed.c();
+    gadcu_store* s = nullptr;
+    check(gadcu_compute_gradients_dp(h_, id.arena, id.index, &v, comm.handle(), &s));
     return Store<T>(s);
   }
 };

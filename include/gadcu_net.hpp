@@ -19,6 +19,8 @@
 //   Map / Then / Using / tuples / Vec<N>        net.rs:382-704    Map / Then / Using / TupleNet / VecNet
 //   SingleOutputNet::add_square_loss, SquareLoss net_ext.rs:17-140 NetBase::add_square_loss, SquareLoss
 //   DiffNet::apply_gradient_step                net_ext.rs:39-73  apply_gradient_step(net, lambda, batch, new_graph)
+//   (none: the reference is one process)                          apply_gradient_step(net, ctx, lambda, batch, comm): the examples
+//                                                                 split over the ranks, update and loss summed before update_weights
 //   Check as an algebra (Value = Dim4)          lib.rs:519-520    CheckAlgebra (values are Dim4; delegates to gadcu::Check)
 //   bincode::serialize(&net.get_weights())      tests/net.rs:136  serialize_weights_bincode / deserialize_weights_bincode
 //
@@ -111,6 +113,23 @@ template <class W, class S> std::vector<W> weights_scale(const std::vector<W>& w
   out.reserve(w.size());
   for (const W& x : w) out.push_back(weights_scale(x, lambda));
   return out;
+}
+
+// the leaves of a weight structure, in order (what a data-parallel step hands to the all-reduce)
+template <class L> void weights_leaves(Unit&, std::vector<L*>&) {}
+template <class L> void weights_leaves(L& leaf, std::vector<L*>& out) { out.push_back(&leaf); }
+template <class A, class B, class L> void weights_leaves(std::pair<A, B>& w, std::vector<L*>& out);
+template <class... W, class L> void weights_leaves(std::tuple<W...>& w, std::vector<L*>& out);
+template <class W, class L> void weights_leaves(std::vector<W>& w, std::vector<L*>& out);
+template <class A, class B, class L> void weights_leaves(std::pair<A, B>& w, std::vector<L*>& out) {
+  weights_leaves(w.first, out);
+  weights_leaves(w.second, out);
+}
+template <class... W, class L> void weights_leaves(std::tuple<W...>& w, std::vector<L*>& out) {
+  std::apply([&](auto&... x) { (weights_leaves(x, out), ...); }, w);
+}
+template <class W, class L> void weights_leaves(std::vector<W>& w, std::vector<L*>& out) {
+  for (W& x : w) weights_leaves(x, out);
 }
 
 // ---- Check as an algebra: values are dims (lib.rs:519-520; the per-family `impl ... for Check` blocks) ----
@@ -453,13 +472,14 @@ class SquareLoss : public NetBase<SquareLoss<N, Data>> {
 // One "mini-batch" gradient step. Per example: a fresh first-order tape from `new_graph()`, the forward pass, the reverse
 // sweep from the (scalar) output with seed 1, `delta += lambda * gradients`; then ONE `update_weights(delta)`. Returns the
 // cumulated output; `Empty` for an empty batch. `lambda` is negative for loss minimisation.
+namespace detail {
+// the per-example body of net_ext.rs:51-67 over batch[first, last)
 template <class N, class T, class NewGraph>
-T apply_gradient_step(N& net, T lambda, const std::vector<typename N::Input>& batch, NewGraph&& new_graph) {
-  std::optional<typename N::Weights> delta;
-  std::optional<T> cumulated_output;
-  for (const auto& example : batch) {
+void accumulate_examples(N& net, T lambda, const std::vector<typename N::Input>& batch, size_t first, size_t last, NewGraph& new_graph,
+                         std::optional<typename N::Weights>& delta, std::optional<T>& cumulated_output) {
+  for (size_t e = first; e < last; e++) {
     auto g = new_graph();  // Graph1::new()
-    auto r = net.eval_with_gradient_info(g, example);
+    auto r = net.eval_with_gradient_info(g, batch[e]);
     const T value = T(r.first.data().item());
     cumulated_output = cumulated_output ? T(*cumulated_output + value) : value;
     auto store = g.evaluate_gradients_once(r.first.gid(), T(1));
@@ -467,6 +487,14 @@ T apply_gradient_step(N& net, T lambda, const std::vector<typename N::Input>& ba
     if (!delta) delta = weights_scale(gradients, lambda);
     else weights_add_assign(*delta, weights_scale(gradients, lambda));
   }
+}
+}  // namespace detail
+
+template <class N, class T, class NewGraph>
+T apply_gradient_step(N& net, T lambda, const std::vector<typename N::Input>& batch, NewGraph&& new_graph) {
+  std::optional<typename N::Weights> delta;
+  std::optional<T> cumulated_output;
+  detail::accumulate_examples(net, lambda, batch, 0, batch.size(), new_graph, delta, cumulated_output);
   if (delta) net.update_weights(*delta);
   if (!cumulated_output) throw Error(ErrorKind::Empty, "Unexpected empty input for apply_gradient_step");
   return *cumulated_output;
@@ -475,6 +503,31 @@ T apply_gradient_step(N& net, T lambda, const std::vector<typename N::Input>& ba
 template <class N, class T>
 T apply_gradient_step(N& net, Context& ctx, T lambda, const std::vector<typename N::Input>& batch) {
   return apply_gradient_step(net, lambda, batch, [&ctx] { return Graph1(ctx); });
+}
+// Over the GPUs of a box (one process each; every rank passes the SAME batch): a rank works on its contiguous share of the
+// examples — the first `batch.size() % nranks` ranks take one more — and the weight update and the loss are summed over the
+// ranks before update_weights, so every rank ends with the same weights. The reference sums per-example gradients
+// (net_ext.rs:62-65): the result differs from the one-process step only by the association of that sum. Returns the loss
+// of the WHOLE batch on every rank. Leaves of N::Weights are Array<T>.
+template <class N, class T>
+T apply_gradient_step(N& net, Context& ctx, T lambda, const std::vector<typename N::Input>& batch, Comm& comm) {
+  if (comm.nranks() <= 1) return apply_gradient_step(net, ctx, lambda, batch);
+  if (batch.empty()) throw Error(ErrorKind::Empty, "Unexpected empty input for apply_gradient_step");
+  const size_t world = size_t(comm.nranks()), rank = size_t(comm.rank());
+  const size_t base = batch.size() / world, extra = batch.size() % world;
+  const size_t first = rank * base + (rank < extra ? rank : extra), last = first + base + (rank < extra ? 1 : 0);
+  std::optional<typename N::Weights> delta;
+  std::optional<T> cumulated_output;
+  auto new_graph = [&ctx] { return Graph1(ctx); };
+  detail::accumulate_examples(net, lambda, batch, first, last, new_graph, delta, cumulated_output);
+  if (!delta) delta = weights_scale(net.get_weights(), T(0));  // a rank without examples contributes zeros
+  Array<T> loss = Array<T>::from_host(ctx, {cumulated_output ? *cumulated_output : T(0)}, Dim4{1});
+  std::vector<Array<T>*> leaves;
+  weights_leaves(*delta, leaves);
+  leaves.push_back(&loss);
+  comm.allreduce_sum(leaves);
+  net.update_weights(*delta);
+  return loss.host()[0];
 }
 
 // ---- checkpoints: the reference's own bytes (tests/net.rs:136-149) ---------------------------------------------------

@@ -26,3 +26,29 @@ def test_reference_net_tests_through_the_cpp_mirror():
         run = subprocess.run([exe], capture_output=True, text=True, timeout=600)
         assert run.returncode == 0, run.stdout + run.stderr
         assert "all net tests passed" in run.stdout
+
+
+def test_data_parallel_net_steps_through_the_cpp_mirror():
+    """gadcu::Comm + apply_gradient_step(net, ctx, lambda, batch, comm): one process per GPU (two ranks), the examples split
+    unevenly (5 over 2), a rank without examples (1 over 2) — losses and weights against the same steps taken alone."""
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs on the box")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "net_cpp")
+        res = build_device_example(exe)
+        assert res.returncode == 0, res.stderr
+        id_file = os.path.join(tmp, "comm_id")
+        procs = [subprocess.Popen([exe, "dp", str(r), "2", id_file], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+        outs = []
+        for p in procs:
+            try:
+                outs.append(p.communicate(timeout=300)[0])
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise
+        for r, (p, out) in enumerate(zip(procs, outs)):
+            assert p.returncode == 0 and f"rank {r}: data-parallel net steps ok" in out, outs
