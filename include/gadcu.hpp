@@ -18,6 +18,8 @@
 //   compute_gradients             graph.rs:307-318        GraphN::compute_gradients(id, seed)
 //   GradientReader::read          store.rs:27-29          Store<T>::get(id) -> std::optional (absent is not zero)
 //   WeightOps                     net.rs:161-180          Array<T>::{add_assign, scale}
+//   Graph<Config1<_>> over per-lane scalars               gadcu::BatchedGraph1<T>: one scalar tape per lane (tests/symbolic.rs:93 is the
+//     (the example loop of net_ext.rs:50-66)                precedent for deriving a tape from another algebra), Store::rerun
 //   (none: the reference is one process)                  gadcu::Comm + Graph1::evaluate_gradients_dp / GraphN::compute_gradients_dp:
 //                                                         the batch split over the GPUs of a box, gradients summed over the ranks
 //
@@ -288,6 +290,22 @@ class Store {
     return Value<T>(out);
   }
   gadcu_store* handle() const { return s_.get(); }
+  // Batched tapes only (BatchedGraph1): the same tapes at new points — `columns[i]` replaces the data of the i-th variable
+  // (creation order) and the compiled lane program runs again, one launch, nothing re-recorded. Returns the variables'
+  // gradient columns (an empty Array where the sweep produced none).
+  std::vector<Array<T>> rerun(const std::vector<Array<T>>& columns) const {
+    std::vector<gadcu_array*> in, out(columns.size(), nullptr);
+    for (const Array<T>& c : columns) in.push_back(c.handle());
+    check(gadcu_batched_rerun(s_.get(), in.data(), in.size(), out.data()));
+    std::vector<Array<T>> gradients;
+    for (gadcu_array* h : out) gradients.push_back(Array<T>::adopt(h));
+    return gradients;
+  }
+  std::pair<uint64_t, uint64_t> program_stats() const {  // (instructions, value slots) of the lane program behind a batched sweep
+    uint64_t instructions = 0, slots = 0;
+    check(gadcu_batched_program_stats(s_.get(), &instructions, &slots));
+    return {instructions, slots};
+  }
 
  private:
   std::shared_ptr<gadcu_store> s_;
@@ -338,6 +356,8 @@ class Algebra {
  public:
   Algebra(Context& ctx, gadcu_algebra_kind kind) : ctx_(&ctx), owned_(true) { check(gadcu_algebra_create(ctx.handle(), kind, &h_)); }
   Algebra(Context& ctx, gadcu_algebra* borrowed) : ctx_(&ctx), h_(borrowed), owned_(false) {}  // the gradient algebra inside a VJP
+  struct Adopt {};
+  Algebra(Context& ctx, gadcu_algebra* owned, Adopt) : ctx_(&ctx), h_(owned), owned_(true) {}  // a handle made by another entry point
   Algebra(const Algebra& o) : ctx_(o.ctx_), owned_(true) { check(gadcu_algebra_clone(o.h_, &h_)); }  // graph.rs:353-360
   Algebra& operator=(const Algebra&) = delete;
   virtual ~Algebra() { if (owned_ && h_) gadcu_algebra_destroy(h_); }
@@ -514,6 +534,7 @@ class Graph1 : public Algebra {
  public:
   explicit Graph1(Context& ctx) : Algebra(ctx, GADCU_GRAPH1) {}
   Graph1(const Graph1&) = default;  // clone(): graph.rs:353-360
+  Graph1(Context& ctx, gadcu_algebra* owned, Adopt a) : Algebra(ctx, owned, a) {}
   template <class T> Store<T> evaluate_gradients(Id id, const Array<T>& seed) const { return sweep(id, seed, 0); }       // graph.rs:263-274
   template <class T> Store<T> evaluate_gradients_once(Id id, const Array<T>& seed) { return sweep(id, seed, 1); }        // graph.rs:277-290
   template <class T, class = std::enable_if_t<std::is_arithmetic<T>::value>>
@@ -539,6 +560,32 @@ class Graph1 : public Algebra {
     check(gadcu_evaluate_gradients(h_, id.arena, id.index, seed.handle(), once, &s));
     return Store<T>(s);
   }
+};
+
+// One scalar Graph1 tape per LANE (gadcu.h "batched scalar tapes"): what the reference does by looping a scalar tape over the
+// examples (net_ext.rs:50-66) runs as one kernel, one lane per thread. Variables and constants are [lanes] columns (structure
+// of arrays); every op only records; evaluate_gradients[_once] with a scalar seed compiles forward + reverse sweep into one
+// per-lane program and launches it. The same generic gad program runs on it and on Graph1 — values handed out here are lazy:
+// `data()` is empty, `force(v)` computes a forward value's column; gradients come out of the store as [lanes] columns.
+template <class T>
+class BatchedGraph1 : public Graph1 {
+ public:
+  BatchedGraph1(Context& ctx, uint64_t lanes) : Graph1(ctx, create(ctx, lanes), Adopt{}), lanes_(lanes) {}
+  uint64_t lanes() const { return lanes_; }
+  Array<T> force(const Value<T>& v) {
+    const gadcu_value c = v.c();
+    gadcu_array* out = nullptr;
+    check(gadcu_batched_force(h_, &c, &out));
+    return Array<T>::adopt(out);
+  }
+
+ private:
+  static gadcu_algebra* create(Context& ctx, uint64_t lanes) {
+    gadcu_algebra* h = nullptr;
+    check(gadcu_batched_create(ctx.handle(), dtype_of<T>::value, lanes, &h));
+    return h;
+  }
+  uint64_t lanes_;
 };
 
 // lib.rs:531-532: higher-order tape, the backward pass is recorded

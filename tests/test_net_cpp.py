@@ -17,8 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="no g++")
 
 
-def build_device_example(out_path):
-    return subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", "net_cpp.cc"),
+def build_device_example(out_path, source="net_cpp.cc"):
+    return subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", source),
                            "-I", os.path.join(ROOT, "include"), "-L", os.path.dirname(_lib.LIB_PATH), "-lgadcu",
                            "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH), "-o", out_path], capture_output=True, text=True)
 
@@ -62,10 +62,13 @@ def test_checkpoint_bytes_equal_the_python_mirror(net_test_exe):
     assert np.array_equal(back[0][0][:, :, 0, 0], w0) and np.array_equal(back[0][1][:, :, 0, 0], eye) and np.array_equal(back[1][:, :, 0, 0], d)
 
 
-def test_device_instantiation_compiles_and_fails_loudly_without_a_gpu():
+@pytest.mark.parametrize("source", ["net_cpp.cc", "rosenbrock_cpp.cc"])
+def test_device_instantiation_compiles_and_fails_loudly_without_a_gpu(source):
+    """examples/net_cpp.cc (the network layer over the device algebra, gadcu::Comm) and examples/rosenbrock_cpp.cc (one generic
+    program on Eval, Graph1 and gadcu::BatchedGraph1) build warning-free against the mirror headers."""
     with tempfile.TemporaryDirectory() as tmp:
-        exe = os.path.join(tmp, "net_cpp")
-        res = build_device_example(exe)
+        exe = os.path.join(tmp, "example")
+        res = build_device_example(exe, source)
         assert res.returncode == 0, res.stderr
         try:
             import torch

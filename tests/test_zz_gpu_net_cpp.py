@@ -28,6 +28,20 @@ def test_reference_net_tests_through_the_cpp_mirror():
         assert "all net tests passed" in run.stdout
 
 
+def test_generic_program_on_scalar_and_batched_tapes_through_the_cpp_mirror():
+    """examples/rosenbrock_cpp.cc: Rosenbrock-N (SURVEY App. D) as ONE generic program on gadcu::Eval, Graph1 (one-element
+    arrays: the scalar tape) and BatchedGraph1 (one tape per lane): known answers, the f64 closed form over 4096 lanes,
+    sampled lanes bit for bit against the scalar tape, Store::rerun == a freshly recorded tape."""
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "rosenbrock_cpp")
+        res = build_device_example(exe, "rosenbrock_cpp.cc")
+        assert res.returncode == 0, res.stderr
+        run = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+        assert run.returncode == 0 and "batched tapes and closed form agree" in run.stdout, run.stdout + run.stderr
+
+
 def test_data_parallel_net_steps_through_the_cpp_mirror():
     """gadcu::Comm + apply_gradient_step(net, ctx, lambda, batch, comm): one process per GPU (two ranks), the examples split
     unevenly (5 over 2), a rank without examples (1 over 2) — losses and weights against the same steps taken alone."""
