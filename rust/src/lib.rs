@@ -615,6 +615,59 @@ impl CuGraphN {
     }
 }
 
+/// One scalar `Graph1` tape per LANE (include/gadcu.h "batched scalar tapes"): what gad does by looping a scalar tape over
+/// the examples (net_ext.rs:50-66) runs as one kernel, one lane per thread. Variables and constants are `[lanes]` columns;
+/// every op only records (`Deref` to `CuGraph1`: the same methods); `evaluate_gradients_once` with a scalar seed compiles
+/// forward + reverse sweep into one per-lane program and launches it. Values handed out are lazy (`data()` holds no
+/// array): `force` computes a forward value's column; gradients come out of the store as `[lanes]` columns. The
+/// derivation has a precedent in the reference: tests/symbolic.rs:93 builds a tape over another algebra the same way.
+pub struct CuBatchedGraph1<T: CuFloat> {
+    tape: CuGraph1,
+    pub lanes: u64,
+    _t: PhantomData<T>,
+}
+impl<T: CuFloat> CuBatchedGraph1<T> {
+    pub fn new(lanes: u64) -> Result<Self> {
+        let mut h = std::ptr::null_mut();
+        to_result(unsafe { gadcu_batched_create(backend().ctx, T::DTYPE, lanes, &mut h) }, "batched_create")?;
+        Ok(CuBatchedGraph1 { tape: CuGraph1 { h }, lanes, _t: PhantomData })
+    }
+    /// The column of a forward value over all lanes.
+    pub fn force(&mut self, v: &CuValue<T>) -> Result<CuArray<T>> {
+        let mut out = std::ptr::null_mut();
+        to_result(unsafe { gadcu_batched_force(self.tape.h, &v.v, &mut out) }, "batched_force")?;
+        Ok(CuArray::from_raw(out))
+    }
+    /// `evaluate_gradients_once(id, T::one())` of every lane's tape at once (graph.rs:277-290).
+    pub fn evaluate_gradients_once(&mut self, id: (u32, u32), seed: T) -> Result<CuStore<T>> {
+        self.tape.evaluate_gradients_once(id, CuArray::from_raw(CuArray::<T>::scalar(seed)))
+    }
+}
+impl<T: CuFloat> std::ops::Deref for CuBatchedGraph1<T> {
+    type Target = CuGraph1;
+    fn deref(&self) -> &CuGraph1 { &self.tape }
+}
+impl<T: CuFloat> std::ops::DerefMut for CuBatchedGraph1<T> {
+    fn deref_mut(&mut self) -> &mut CuGraph1 { &mut self.tape }
+}
+impl<T: CuFloat> CuStore<T> {
+    /// Batched sweeps only: the same tapes at new points — `columns[i]` replaces the data of the i-th variable (creation
+    /// order) and the compiled lane program runs again, one launch, nothing re-recorded. The variables' gradient columns,
+    /// `None` where the sweep produced none.
+    pub fn rerun(&self, columns: &[&CuArray<T>]) -> Result<Vec<Option<CuArray<T>>>> {
+        let raw: Vec<*mut gadcu_array> = columns.iter().map(|c| c.h).collect();
+        let mut out: Vec<*mut gadcu_array> = vec![std::ptr::null_mut(); raw.len()];
+        to_result(unsafe { gadcu_batched_rerun(self.h, raw.as_ptr(), raw.len(), out.as_mut_ptr()) }, "batched_rerun")?;
+        Ok(out.into_iter().map(|h| if h.is_null() { None } else { Some(CuArray::from_raw(h)) }).collect())
+    }
+    /// (instructions, value slots) of the lane program behind a batched sweep.
+    pub fn program_stats(&self) -> (u64, u64) {
+        let (mut a, mut b) = (0u64, 0u64);
+        unsafe { gadcu_batched_program_stats(self.h, &mut a, &mut b); }
+        (a, b)
+    }
+}
+
 /// Backend switches with no counterpart in gad (include/gadcu.h): fused GEMM epilogues (0 never, 1 where it pays, 2 always)
 /// and automatic CUDA-graph replay keyed by the recorded kernel sequence (the tape is still rebuilt every step).
 pub fn set_gemm_epilogue(mode: i32) { unsafe { gadcu_ctx_set_gemm_epilogue(backend().ctx, mode); } }
