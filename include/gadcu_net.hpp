@@ -504,6 +504,14 @@ template <class N, class T>
 T apply_gradient_step(N& net, Context& ctx, T lambda, const std::vector<typename N::Input>& batch) {
   return apply_gradient_step(net, lambda, batch, [&ctx] { return Graph1(ctx); });
 }
+// [first, last) of `rank`'s contiguous share of `total` units: the first `total % world` ranks take one more
+// (the same split as gad_b200/dp.py: shard_bounds)
+inline std::pair<size_t, size_t> shard_bounds(size_t total, size_t world, size_t rank) {
+  if (world < 1 || rank >= world) throw Error(ErrorKind::Invalid, "shard_bounds: rank " + std::to_string(rank) + " of " + std::to_string(world));
+  const size_t base = total / world, extra = total % world;
+  const size_t first = rank * base + (rank < extra ? rank : extra);
+  return {first, first + base + (rank < extra ? 1 : 0)};
+}
 // Over the GPUs of a box (one process each; every rank passes the SAME batch): a rank works on its contiguous share of the
 // examples — the first `batch.size() % nranks` ranks take one more — and the weight update and the loss are summed over the
 // ranks before update_weights, so every rank ends with the same weights. The reference sums per-example gradients
@@ -513,9 +521,8 @@ template <class N, class T>
 T apply_gradient_step(N& net, Context& ctx, T lambda, const std::vector<typename N::Input>& batch, Comm& comm) {
   if (comm.nranks() <= 1) return apply_gradient_step(net, ctx, lambda, batch);
   if (batch.empty()) throw Error(ErrorKind::Empty, "Unexpected empty input for apply_gradient_step");
-  const size_t world = size_t(comm.nranks()), rank = size_t(comm.rank());
-  const size_t base = batch.size() / world, extra = batch.size() % world;
-  const size_t first = rank * base + (rank < extra ? rank : extra), last = first + base + (rank < extra ? 1 : 0);
+  const std::pair<size_t, size_t> share = shard_bounds(batch.size(), size_t(comm.nranks()), size_t(comm.rank()));
+  const size_t first = share.first, last = share.second;
   std::optional<typename N::Weights> delta;
   std::optional<T> cumulated_output;
   auto new_graph = [&ctx] { return Graph1(ctx); };

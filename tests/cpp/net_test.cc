@@ -350,7 +350,49 @@ static void test_combinators_and_weight_structures() {
   EXPECT(back.size() == 2 && close(back[1], kI, 0.0f));
 }
 
+// a corrupt checkpoint is an Error, never a crash or a wild allocation (the build runs under ASan + UBSan)
+static void test_corrupt_checkpoints_are_errors() {
+  using W = std::tuple<std::vector<L>, std::pair<Unit, host::Leaf<double>>>;
+  const W w{std::vector<L>{kW0, kI, L({1, 2}, Dim4{2, 1})}, {Unit{}, host::Leaf<double>({0.25, -3.0, 8.0, 1e300}, Dim4{2, 2})}};
+  const std::vector<uint8_t> good = serialize_weights_bincode(w);
+  HostMaker maker;
+  const W back = deserialize_weights_bincode<W>(maker, good);
+  EXPECT(serialize_weights_bincode(back) == good);
+  uint64_t state = 0x9E3779B97F4A7C15ull;
+  auto next = [&] { state ^= state << 13; state ^= state >> 7; state ^= state << 17; return state; };
+  int accepted = 0, rejected = 0;
+  for (int trial = 0; trial < 4000; trial++) {
+    std::vector<uint8_t> bad = good;
+    switch (trial % 4) {
+      case 0: bad.resize(next() % good.size()); break;                                             // truncated anywhere
+      case 1: bad[next() % bad.size()] ^= uint8_t(1u << (next() % 8)); break;                      // one flipped bit
+      case 2: for (int k = 0; k < 8; k++) bad[next() % bad.size()] = uint8_t(next()); break;       // a few random bytes
+      default: bad.insert(bad.begin() + long(next() % bad.size()), size_t(1 + next() % 16), uint8_t(next())); break;  // inserted junk
+    }
+    try {
+      const W got = deserialize_weights_bincode<W>(maker, bad);
+      accepted++;  // (a flipped data bit is still a well-formed blob)
+      EXPECT(serialize_weights_bincode(got) == bad);
+    } catch (const Error& e) {
+      rejected++;
+      EXPECT(e.kind == ErrorKind::Invalid || e.kind == ErrorKind::Type);
+    }
+  }
+  EXPECT(accepted > 0 && rejected > 1000);
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && !std::strcmp(argv[1], "shards")) {  // `total world` per line on stdin -> every rank's [first, last)
+    unsigned long total, world;
+    while (std::scanf("%lu %lu", &total, &world) == 2) {
+      for (size_t r = 0; r < world; r++) {
+        const auto b = shard_bounds(total, world, r);
+        std::printf("%zu %zu ", b.first, b.second);
+      }
+      std::printf("\n");
+    }
+    return 0;
+  }
   if (argc > 1 && !std::strcmp(argv[1], "hex")) {  // the checkpoint bytes of ((), W0) followed by those of [W0 (f32), 2x1 f64]
     for (uint8_t b : serialize_weights_bincode(std::make_pair(Unit{}, kW0))) std::printf("%02x", b);
     std::printf("\n");
@@ -365,6 +407,7 @@ int main(int argc, char** argv) {
     test_gradient_step_closed_form();
     test_weight_snapshot_is_a_value();
     test_combinators_and_weight_structures();
+    test_corrupt_checkpoints_are_errors();
   } catch (const Error& e) {
     std::printf("FAILED with gadcu::Error kind %d: %s\n", int(e.kind), e.what());
     return 2;

@@ -62,6 +62,20 @@ def test_checkpoint_bytes_equal_the_python_mirror(net_test_exe):
     assert np.array_equal(back[0][0][:, :, 0, 0], w0) and np.array_equal(back[0][1][:, :, 0, 0], eye) and np.array_equal(back[1][:, :, 0, 0], d)
 
 
+def test_shares_of_a_batch_equal_the_python_mirror(net_test_exe):
+    """gadcu::net::shard_bounds (who works on which examples of a data-parallel step) against gad_b200.dp.shard_bounds."""
+    from gad_b200 import dp
+    cases = [(t, w) for w in (1, 2, 3, 4, 7, 8) for t in (0, 1, 2, 5, 8, 63, 64, 1000, 8192)]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0")
+    run = subprocess.run([net_test_exe, "shards"], input="".join(f"{t} {w}\n" for t, w in cases), capture_output=True, text=True, timeout=60, env=env)
+    assert run.returncode == 0, run.stdout + run.stderr
+    lines = run.stdout.strip().split("\n")
+    assert len(lines) == len(cases)
+    for (t, w), line in zip(cases, lines):
+        got = [int(x) for x in line.split()]
+        assert list(zip(got[0::2], got[1::2])) == dp.all_shards(t, w), (t, w)
+
+
 @pytest.mark.parametrize("source", ["net_cpp.cc", "rosenbrock_cpp.cc"])
 def test_device_instantiation_compiles_and_fails_loudly_without_a_gpu(source):
     """examples/net_cpp.cc (the network layer over the device algebra, gadcu::Comm) and examples/rosenbrock_cpp.cc (one generic
